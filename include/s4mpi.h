@@ -1,0 +1,177 @@
+/*
+ * libs4mpi -- C-ABI of the B200-native Streets4MPI traffic-assignment hot path.
+ *
+ * The reference (jfietkau/Streets4MPI) has no FFI layer: its hot path is the
+ * Python method surface of Simulation / StreetNetwork plus one MPI collective.
+ * Every entry point below names the reference lines it replaces (paths relative
+ * to the reference checkout).  The host side (the streets4mpi_b200 package) keeps the
+ * reference's class and method names and forwards to these through ctypes; the
+ * stub a reference maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / CUDA types in signatures (a CUDA
+ *     stream crosses as void*).
+ *   - every function returns S4_OK (0) or a negative S4_ERR_*; the message of
+ *     the last failure on the calling thread is s4_last_error().  No exceptions,
+ *     no exit().
+ *   - node ids are dense int32 0..V-1, assigned by the host in ascending order
+ *     of the original ids (so id-based tie-breaks commute with the mapping);
+ *     street ids are the reference's street_index 0..S-1 (streetnetwork.py:40,57).
+ *   - host arrays are borrowed for the duration of the call only.
+ *   - one host thread drives one s4_ctx; work is stream-ordered on the ctx
+ *     stream and asynchronous unless a function hands results back to the host.
+ *   - there is NO CPU fallback: without a CUDA device every call fails with
+ *     S4_ERR_CUDA.
+ */
+#ifndef S4MPI_H
+#define S4MPI_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define S4_ABI_VERSION 1
+
+#define S4_OK 0
+#define S4_ERR_ARG (-1)    /* bad argument (null pointer, id out of range, ...) */
+#define S4_ERR_CUDA (-2)   /* CUDA runtime error, or no device */
+#define S4_ERR_OOM (-3)    /* host or device allocation failed */
+#define S4_ERR_STATE (-4)  /* call not valid in the current state */
+
+typedef struct s4_ctx s4_ctx;     /* one GPU + one stream                                   */
+typedef struct s4_graph s4_graph; /* replicated street graph: symmetric CSR in HBM          */
+typedef struct s4_sim s4_sim;     /* one (virtual) MPI rank: trips, jam tolerance, loads    */
+
+/* settings.py:36-44 -- the knobs the hot path reads */
+typedef struct s4_physics {
+    double car_length;            /* settings["car_length"]            (simulation.py:132) */
+    double min_breaking_distance; /* settings["min_breaking_distance"] (simulation.py:132) */
+    double braking_deceleration;  /* settings["braking_deceleration"]  (simulation.py:134) */
+    uint32_t trip_volume;         /* settings["trip_volume"]           (simulation.py:86)  */
+    uint32_t reserved;
+} s4_physics;
+
+/* which endpoint of a trip roots its shortest-path tree */
+#define S4_ROOT_ORIGIN 0 /* reference grouping: one tree per distinct origin (simulation.py:71) */
+#define S4_ROOT_GOAL 1   /* tree per distinct goal; identical loads where paths are unique       */
+#define S4_ROOT_AUTO 2   /* whichever endpoint set is smaller (the graph is undirected)          */
+
+/* device-side work and time accounting since the last s4_sim_reset_counters */
+typedef struct s4_counters {
+    uint64_t days;              /* s4_sim_step calls                                              */
+    uint64_t sssp_instances;    /* shortest-path trees computed                                   */
+    uint64_t arcs_algorithmic;  /* sum over trees of arcs out of reachable nodes (each arc once)  */
+    uint64_t nodes_algorithmic; /* sum over trees of reachable nodes                              */
+    uint64_t arcs_relaxed;      /* arcs actually scanned, re-relaxations included                 */
+    uint64_t nodes_popped;      /* frontier entries expanded                                      */
+    uint64_t stale_pops;        /* frontier entries skipped as superseded                         */
+    uint64_t queue_pushes;      /* near + far insertions                                          */
+    uint64_t bucket_advances;   /* far-pile splits                                                */
+    uint64_t relax_rounds;      /* CTA-wide relaxation rounds                                     */
+    uint64_t fallback_sweeps;   /* Bellman-Ford sweeps after a queue overflow (normally 0)        */
+    uint64_t trips_routed;      /* trips handed to the walk (reachable or not)                    */
+    uint64_t trips_unreachable; /* goal not in the tree (simulation.py:80)                        */
+    uint64_t trips_stuck;       /* no predecessor found (zero-weight plateau); normally 0         */
+    uint64_t hops;              /* street traversals == sum of load increments / trip_volume      */
+    uint64_t kernel_launches;   /* kernels this library launched                                  */
+    uint64_t sssp_launches;     /* launches of the SSSP kernel                                    */
+    double ms_weights;          /* K1 (CUDA events, summed)                                       */
+    double ms_sssp;             /* K2                                                             */
+    double ms_walk;             /* K3                                                             */
+    double ms_adapt;            /* K5                                                             */
+    double ms_step_total;       /* whole s4_sim_step, first kernel to last                        */
+} s4_counters;
+
+int s4_abi_version(void);
+const char *s4_last_error(void);
+
+/* ---- context ------------------------------------------------------------ */
+/* Replaces the per-process setup of streets4mpi.py:44-46.  `stream` is a
+ * cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream) or NULL to let
+ * the library create its own non-blocking stream. */
+int s4_ctx_create(int device, void *stream, s4_ctx **out);
+int s4_ctx_destroy(s4_ctx *ctx);
+int s4_ctx_sync(s4_ctx *ctx);
+/* Tunables (all have defaults): "delta_factor" (bucket width in mean arc
+ * weights), "block_threads" (256|512|1024), "tile" (lanes per frontier node:
+ * 2|4|8), "ctas_per_sm", "near_smem_entries", "queue_entries", "batch_roots",
+ * "pool_bytes", "root_mode" (S4_ROOT_*), "walk_tile" (4|8|16|32). */
+int s4_ctx_set_option(s4_ctx *ctx, const char *key, double value);
+int s4_ctx_get_option(s4_ctx *ctx, const char *key, double *value);
+/* name, SM count, bytes of HBM; name_out may be NULL */
+int s4_ctx_device_info(s4_ctx *ctx, char *name_out, int name_cap, int *sm_count, uint64_t *hbm_bytes);
+
+/* ---- graph (streetnetwork.py:35-57, 113-125) ------------------------------ */
+/* Street i joins u[i] and v[i] (either orientation, the graph is undirected:
+ * streetnetwork.py:24,37), has length[i] metres and speed limit max_speed[i]
+ * km/h (> 0).  Builds the symmetric CSR (2 arcs per street, arcs of a node in
+ * street_index order) and uploads it. */
+int s4_graph_upload(s4_ctx *ctx, int32_t V, int64_t S, const int32_t *u, const int32_t *v,
+                    const double *length, const int32_t *max_speed, s4_graph **out);
+int s4_graph_free(s4_graph *g);
+int s4_graph_dims(s4_graph *g, int32_t *V, int64_t *S, int64_t *A);
+/* StreetNetwork.calculate_shortest_paths (streetnetwork.py:108-109) with
+ * explicit per-street weights (the network's current driving times,
+ * streetnetwork.py:60-61).  dist_out[V] (+inf = unreachable), pred_out[V]
+ * (-1 for the origin and for unreachable nodes); either may be NULL.
+ * Predecessor rule: lowest neighbour id among those reproducing dist exactly. */
+int s4_graph_sssp(s4_graph *g, const double *w_street, int32_t origin, double *dist_out, int32_t *pred_out);
+
+/* ---- simulation = one (virtual) rank (simulation.py:37-45, streets4mpi.py:67-82) */
+/* T trips (origin[i] -> goal[i]); jam_tolerance as drawn at streets4mpi.py:78.
+ * Trips are grouped by tree root on the device (tripgenerator.py:37-42 did that
+ * with a dict).  The simulation owns a private copy of the speed limits, like
+ * every reference rank owns its StreetNetwork. */
+int s4_sim_create(s4_graph *g, int64_t T, const int32_t *origin, const int32_t *goal,
+                  double jam_tolerance, const s4_physics *phys, s4_sim **out);
+int s4_sim_free(s4_sim *sim);
+/* number of distinct tree roots and the root mode actually used */
+int s4_sim_roots(s4_sim *sim, int64_t *n_roots, int *root_mode);
+
+/* Simulation.step (simulation.py:48-88): weights from the resident traffic_load
+ * (:53-65), reset it (:68), one tree per root (:71-75), walk every trip and add
+ * trip_volume per street (:78-88).  Asynchronous. */
+int s4_sim_step(s4_sim *sim);
+/* The per-street driving times (simulation.py:53-65).  refresh != 0: run K1 alone
+ * on the resident load without resetting it; refresh == 0: the weights the last
+ * step (or refresh) routed on.  w_out[S] may be NULL. */
+int s4_sim_weights(s4_sim *sim, int refresh, double *w_out);
+
+/* `simulation.traffic_load` (uint32[S], array('I')): read (D2H) / assign (H2D,
+ * streets4mpi.py:99) / device address for an in-place collective (:97-98). */
+int s4_sim_get_load(s4_sim *sim, uint32_t *out);
+int s4_sim_set_load(s4_sim *sim, const uint32_t *in);
+void *s4_sim_load_device_ptr(s4_sim *sim);
+/* dst.load += src.load  /  dst.load = src.load -- several virtual ranks on one GPU */
+int s4_sim_load_add(s4_sim *dst, s4_sim *src);
+int s4_sim_load_copy(s4_sim *dst, s4_sim *src);
+/* streets4mpi.py:100 + utils.py:26-34: cumulative = load + (cumulative or 0) */
+int s4_sim_commit_total(s4_sim *sim);
+/* `simulation.cumulative_traffic_load`: *is_none = 1 when it is None */
+int s4_sim_get_cumulative(s4_sim *sim, uint32_t *out, int *is_none);
+int s4_sim_set_cumulative(s4_sim *sim, const uint32_t *in_or_null);
+
+/* Simulation.road_construction (simulation.py:91-109, streetnetwork.py:79-82):
+ * rank streets by (cumulative load, street_index), apply the literal sweep,
+ * clamp to [1,140], cumulative = None.  adaptable[S] (may be NULL = all) marks
+ * the streets whose change is visible to the weight loop (insertion orientation
+ * u <= v, see DESIGN.md "orientation aliasing"); every street's
+ * insertion-orientation value changes regardless. */
+int s4_sim_road_construction(s4_sim *sim, const uint8_t *adaptable);
+/* speed limits as the weight loop sees them / as stored on the insertion orientation */
+int s4_sim_get_max_speed(s4_sim *sim, int32_t *visible_out, int32_t *insertion_out);
+int s4_sim_set_max_speed(s4_sim *sim, const int32_t *visible, const int32_t *insertion_or_null);
+
+int s4_sim_get_counters(s4_sim *sim, s4_counters *out);
+int s4_sim_reset_counters(s4_sim *sim);
+
+/* calculate_driving_speed (simulation.py:129-138) for n streets, on the device */
+int s4_driving_speed(s4_ctx *ctx, int64_t n, const double *length, const int32_t *max_speed,
+                     const uint32_t *trips, const s4_physics *phys, double *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* S4MPI_H */

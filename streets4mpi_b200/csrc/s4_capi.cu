@@ -1,0 +1,1065 @@
+// libs4mpi: C-ABI (include/s4mpi.h) and host-side orchestration of the kernels in
+// s4_kernels.cuh.  One s4_ctx = one GPU + one stream; all work is stream-ordered.
+// There is no CPU fallback anywhere in this file: every entry point either runs
+// the CUDA path or reports an error.
+#include "../../include/s4mpi.h"
+#include "s4_kernels.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <numeric>
+#include <string>
+#include <vector>
+
+using namespace s4;
+
+// ---------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(expr)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e__ = (expr);                                                                      \
+        if (e__ != cudaSuccess)                                                                        \
+            return fail(e__ == cudaErrorMemoryAllocation ? S4_ERR_OOM : S4_ERR_CUDA, "%s:%d %s -> %s", \
+                        __FILE__, __LINE__, #expr, cudaGetErrorString(e__));                           \
+    } while (0)
+
+#define CHECK_ARG(cond, msg)                          \
+    do {                                              \
+        if (!(cond)) return fail(S4_ERR_ARG, "%s", msg); \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// objects
+// ---------------------------------------------------------------------------
+struct Options {
+    double delta_factor = 2.0;
+    int block_threads = 512;
+    int tile = 4;
+    int ctas_per_sm = 2;
+    int near_smem_entries = 4096;
+    int64_t queue_entries = 0;      // 0 = auto (from V)
+    int64_t batch_roots = 0;        // 0 = auto (from pool_bytes)
+    double pool_bytes = 24.0e9;
+    int root_mode = S4_ROOT_ORIGIN;
+    int walk_tile = 8;
+};
+
+struct s4_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaDeviceProp prop;
+    Options opt;
+};
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count)
+    {
+        release();
+        n = count;
+        if (count == 0) return cudaSuccess;
+        return cudaMalloc(&p, count * sizeof(T));
+    }
+    cudaError_t ensure(size_t count) { return count <= n && p ? cudaSuccess : alloc(count); }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    ~DevBuf() { release(); }
+};
+
+struct EvPair {
+    cudaEvent_t a = nullptr, b = nullptr;
+};
+
+struct s4_graph {
+    s4_ctx *ctx = nullptr;
+    int32_t V = 0;
+    int64_t S = 0, A = 0;
+    DevBuf<u32> row_ptr;       // V+1
+    DevBuf<uint2> arc_cs;      // A  {head, street}
+    DevBuf<double> length;     // S
+    std::vector<int32_t> max_speed0;   // host copy of the uploaded limits
+    // connected components (host): algorithmic arcs / nodes of a tree rooted at r
+    std::vector<int32_t> comp_of;
+    std::vector<int64_t> comp_arcs, comp_nodes;
+    // scratch shared by every simulation on this graph (sized lazily)
+    DevBuf<u64> pool;          // slots * V
+    int64_t pool_slots = 0;
+    DevBuf<uint2> ws_near, ws_far;
+    int ws_ctas = 0;
+    u32 near_gcap = 0, far_cap = 0;
+    DevBuf<u32> work_counters;
+    // single-source API scratch
+    DevBuf<Arc> arcs_tmp;
+    DevBuf<double> w_tmp;
+    DevBuf<int32_t> pred_tmp;
+    DevBuf<int32_t> root_tmp;
+    DevBuf<u64> ctr_tmp;
+    DevBuf<double> wsum_tmp;
+};
+
+struct s4_sim {
+    s4_graph *g = nullptr;
+    int64_t T = 0, D = 0;
+    int root_mode = S4_ROOT_ORIGIN;
+    double jam = 0.0;
+    Phys ph{};
+    u32 volume = 1;
+    DevBuf<int32_t> trip_target;   // T, sorted by root
+    DevBuf<u32> trip_root;         // T
+    DevBuf<int32_t> roots;         // D
+    std::vector<int64_t> h_root_off;   // D+1
+    int64_t alg_arcs_per_day = 0, alg_nodes_per_day = 0;
+    DevBuf<u32> load, cum;
+    bool has_cum = false;
+    DevBuf<int32_t> ms_vis, ms_ins;
+    DevBuf<double> w_street;
+    DevBuf<Arc> arcs;
+    DevBuf<double> wsum;
+    DevBuf<u64> counters;
+    bool weights_valid = false;
+    // sort scratch for K5
+    DevBuf<u32> sort_keys, sort_vals, sort_keys_out, order;
+    DevBuf<unsigned char> cub_tmp;
+    DevBuf<uint8_t> mask;
+    // timing
+    std::vector<EvPair> ev_w, ev_sssp, ev_walk, ev_adapt, ev_step;
+    size_t used_w = 0, used_sssp = 0, used_walk = 0, used_adapt = 0, used_step = 0;
+    s4_counters acc{};
+};
+
+static int grid_for(int64_t n, int block, const s4_ctx *ctx)
+{
+    int64_t need = (n + block - 1) / block;
+    int64_t cap = (int64_t)ctx->prop.multiProcessorCount * 8;
+    return (int)std::max<int64_t>(1, std::min(need, cap));
+}
+
+// ---------------------------------------------------------------------------
+// misc entry points
+// ---------------------------------------------------------------------------
+extern "C" int s4_abi_version(void) { return S4_ABI_VERSION; }
+extern "C" const char *s4_last_error(void) { return g_err; }
+
+extern "C" int s4_ctx_create(int device, void *stream, s4_ctx **out)
+{
+    CHECK_ARG(out, "s4_ctx_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(S4_ERR_CUDA, "no CUDA device (%s); libs4mpi has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    CHECK_ARG(device >= 0 && device < ndev, "s4_ctx_create: device out of range");
+    CU(cudaSetDevice(device));
+    s4_ctx *c = new (std::nothrow) s4_ctx();
+    if (!c) return fail(S4_ERR_OOM, "host allocation failed");
+    c->device = device;
+    cudaError_t pe = cudaGetDeviceProperties(&c->prop, device);
+    if (pe != cudaSuccess) { delete c; return fail(S4_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(pe)); }
+    if (stream) {
+        c->stream = (cudaStream_t)stream;
+    } else {
+        cudaError_t se = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (se != cudaSuccess) { delete c; return fail(S4_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(se)); }
+        c->own_stream = true;
+    }
+    *out = c;
+    return S4_OK;
+}
+
+extern "C" int s4_ctx_destroy(s4_ctx *ctx)
+{
+    if (!ctx) return S4_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return S4_OK;
+}
+
+extern "C" int s4_ctx_sync(s4_ctx *ctx)
+{
+    CHECK_ARG(ctx, "s4_ctx_sync: ctx is NULL");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return S4_OK;
+}
+
+static void option_slot(Options &o, const char *key, int *kind, void **raw)
+{
+    // kind: 0 double, 1 int, 2 int64
+    struct Item { const char *k; int kind; void *p; };
+    Item items[] = {
+        {"delta_factor", 0, &o.delta_factor},       {"block_threads", 1, &o.block_threads},
+        {"tile", 1, &o.tile},                       {"ctas_per_sm", 1, &o.ctas_per_sm},
+        {"near_smem_entries", 1, &o.near_smem_entries}, {"queue_entries", 2, &o.queue_entries},
+        {"batch_roots", 2, &o.batch_roots},         {"pool_bytes", 0, &o.pool_bytes},
+        {"root_mode", 1, &o.root_mode},             {"walk_tile", 1, &o.walk_tile},
+    };
+    for (auto &it : items)
+        if (strcmp(it.k, key) == 0) { *kind = it.kind; *raw = it.p; return; }
+    *raw = nullptr;
+}
+
+extern "C" int s4_ctx_set_option(s4_ctx *ctx, const char *key, double value)
+{
+    CHECK_ARG(ctx && key, "s4_ctx_set_option: NULL argument");
+    int kind = 0;
+    void *raw = nullptr;
+    option_slot(ctx->opt, key, &kind, &raw);
+    if (!raw) return fail(S4_ERR_ARG, "unknown option '%s'", key);
+    Options trial = ctx->opt;
+    option_slot(trial, key, &kind, &raw);
+    if (kind == 0) *(double *)raw = value;
+    else if (kind == 1) *(int *)raw = (int)value;
+    else *(int64_t *)raw = (int64_t)value;
+    const Options &t = trial;
+    bool ok = t.delta_factor >= 0.0 && (t.block_threads == 256 || t.block_threads == 512 || t.block_threads == 1024) &&
+              (t.tile == 2 || t.tile == 4 || t.tile == 8) && t.ctas_per_sm >= 1 && t.ctas_per_sm <= 8 &&
+              t.near_smem_entries >= 64 && t.near_smem_entries <= 13000 && t.queue_entries >= 0 &&
+              t.batch_roots >= 0 && t.pool_bytes >= 0.0 && t.root_mode >= 0 && t.root_mode <= 2 &&
+              (t.walk_tile == 4 || t.walk_tile == 8 || t.walk_tile == 16 || t.walk_tile == 32);
+    if (!ok) return fail(S4_ERR_ARG, "option '%s': value %g out of range", key, value);
+    ctx->opt = trial;
+    return S4_OK;
+}
+
+extern "C" int s4_ctx_get_option(s4_ctx *ctx, const char *key, double *value)
+{
+    CHECK_ARG(ctx && key && value, "s4_ctx_get_option: NULL argument");
+    int kind = 0;
+    void *raw = nullptr;
+    option_slot(ctx->opt, key, &kind, &raw);
+    if (!raw) return fail(S4_ERR_ARG, "unknown option '%s'", key);
+    *value = kind == 0 ? *(double *)raw : kind == 1 ? (double)*(int *)raw : (double)*(int64_t *)raw;
+    return S4_OK;
+}
+
+extern "C" int s4_ctx_device_info(s4_ctx *ctx, char *name_out, int name_cap, int *sm_count, uint64_t *hbm_bytes)
+{
+    CHECK_ARG(ctx, "s4_ctx_device_info: ctx is NULL");
+    if (name_out && name_cap > 0) snprintf(name_out, (size_t)name_cap, "%s", ctx->prop.name);
+    if (sm_count) *sm_count = ctx->prop.multiProcessorCount;
+    if (hbm_bytes) *hbm_bytes = (uint64_t)ctx->prop.totalGlobalMem;
+    return S4_OK;
+}
+
+// ---------------------------------------------------------------------------
+// graph
+// ---------------------------------------------------------------------------
+static int32_t uf_find(std::vector<int32_t> &parent, int32_t x)
+{
+    while (parent[x] != x) {
+        parent[x] = parent[parent[x]];
+        x = parent[x];
+    }
+    return x;
+}
+
+extern "C" int s4_graph_upload(s4_ctx *ctx, int32_t V, int64_t S, const int32_t *u, const int32_t *v,
+                               const double *length, const int32_t *max_speed, s4_graph **out)
+{
+    CHECK_ARG(ctx && out, "s4_graph_upload: NULL argument");
+    *out = nullptr;
+    CHECK_ARG(V > 0, "s4_graph_upload: V must be positive");
+    CHECK_ARG(S >= 0 && S < (int64_t)1 << 31, "s4_graph_upload: S out of range");
+    CHECK_ARG(S == 0 || (u && v && length && max_speed), "s4_graph_upload: NULL street array");
+    CU(cudaSetDevice(ctx->device));
+    std::vector<u32> row_ptr((size_t)V + 1, 0u);
+    for (int64_t s = 0; s < S; ++s) {
+        if (u[s] < 0 || u[s] >= V || v[s] < 0 || v[s] >= V) return fail(S4_ERR_ARG, "street %lld: node id out of range", (long long)s);
+        if (!(length[s] >= 0.0) || std::isinf(length[s])) return fail(S4_ERR_ARG, "street %lld: length must be finite and >= 0", (long long)s);
+        if (max_speed[s] < 1) return fail(S4_ERR_ARG, "street %lld: max_speed must be >= 1", (long long)s);
+        ++row_ptr[(size_t)u[s] + 1];
+        if (u[s] != v[s]) ++row_ptr[(size_t)v[s] + 1];
+    }
+    uint64_t total = 0;
+    for (int32_t i = 0; i < V; ++i) {
+        total += row_ptr[(size_t)i + 1];
+        if (total >= 0xFFFFFFFFull) return fail(S4_ERR_ARG, "too many arcs for 32-bit offsets");
+        row_ptr[(size_t)i + 1] = (u32)total;
+    }
+    const int64_t A = (int64_t)total;
+    std::vector<uint2> arc_cs((size_t)A);
+    {
+        std::vector<u32> fill(row_ptr.begin(), row_ptr.end() - 1);
+        for (int64_t s = 0; s < S; ++s) {                        // street_index order inside every row
+            arc_cs[fill[(size_t)u[s]]++] = make_uint2((u32)v[s], (u32)s);
+            if (u[s] != v[s]) arc_cs[fill[(size_t)v[s]]++] = make_uint2((u32)u[s], (u32)s);
+        }
+    }
+    s4_graph *g = new (std::nothrow) s4_graph();
+    if (!g) return fail(S4_ERR_OOM, "host allocation failed");
+    g->ctx = ctx;
+    g->V = V;
+    g->S = S;
+    g->A = A;
+    g->max_speed0.assign(max_speed, max_speed + S);
+    // connected components -> algorithmic work of a tree (each arc of the
+    // root's component is scanned exactly once by any exact SSSP)
+    {
+        std::vector<int32_t> parent((size_t)V);
+        std::iota(parent.begin(), parent.end(), 0);
+        for (int64_t s = 0; s < S; ++s) {
+            int32_t a = uf_find(parent, u[s]), b = uf_find(parent, v[s]);
+            if (a != b) parent[(size_t)std::max(a, b)] = std::min(a, b);
+        }
+        g->comp_of.resize((size_t)V);
+        g->comp_arcs.assign((size_t)V, 0);
+        g->comp_nodes.assign((size_t)V, 0);
+        for (int32_t i = 0; i < V; ++i) {
+            int32_t r = uf_find(parent, i);
+            g->comp_of[(size_t)i] = r;
+            g->comp_nodes[(size_t)r] += 1;
+            g->comp_arcs[(size_t)r] += row_ptr[(size_t)i + 1] - row_ptr[(size_t)i];
+        }
+    }
+    auto bail = [&](cudaError_t e, const char *what) {
+        delete g;
+        return fail(e == cudaErrorMemoryAllocation ? S4_ERR_OOM : S4_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    };
+    cudaError_t e;
+    if ((e = g->row_ptr.alloc((size_t)V + 1)) != cudaSuccess) return bail(e, "alloc row_ptr");
+    if ((e = g->arc_cs.alloc((size_t)std::max<int64_t>(A, 1))) != cudaSuccess) return bail(e, "alloc arcs");
+    if ((e = g->length.alloc((size_t)std::max<int64_t>(S, 1))) != cudaSuccess) return bail(e, "alloc length");
+    if ((e = cudaMemcpyAsync(g->row_ptr.p, row_ptr.data(), ((size_t)V + 1) * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) return bail(e, "copy row_ptr");
+    if (A > 0 && (e = cudaMemcpyAsync(g->arc_cs.p, arc_cs.data(), (size_t)A * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) return bail(e, "copy arcs");
+    if (S > 0 && (e = cudaMemcpyAsync(g->length.p, length, (size_t)S * sizeof(double), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) return bail(e, "copy length");
+    if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return bail(e, "sync");
+    *out = g;
+    return S4_OK;
+}
+
+extern "C" int s4_graph_free(s4_graph *g)
+{
+    if (!g) return S4_OK;
+    cudaSetDevice(g->ctx->device);
+    cudaStreamSynchronize(g->ctx->stream);
+    delete g;
+    return S4_OK;
+}
+
+extern "C" int s4_graph_dims(s4_graph *g, int32_t *V, int64_t *S, int64_t *A)
+{
+    CHECK_ARG(g, "s4_graph_dims: graph is NULL");
+    if (V) *V = g->V;
+    if (S) *S = g->S;
+    if (A) *A = g->A;
+    return S4_OK;
+}
+
+// ---------------------------------------------------------------------------
+// SSSP launch plumbing
+// ---------------------------------------------------------------------------
+typedef void (*SsspKernel)(SsspParams);
+
+static SsspKernel pick_sssp(int block, int tile)
+{
+    switch (block * 16 + tile) {
+        case 256 * 16 + 2: return sssp_nearfar_kernel<256, 2>;
+        case 256 * 16 + 4: return sssp_nearfar_kernel<256, 4>;
+        case 256 * 16 + 8: return sssp_nearfar_kernel<256, 8>;
+        case 512 * 16 + 2: return sssp_nearfar_kernel<512, 2>;
+        case 512 * 16 + 4: return sssp_nearfar_kernel<512, 4>;
+        case 512 * 16 + 8: return sssp_nearfar_kernel<512, 8>;
+        case 1024 * 16 + 2: return sssp_nearfar_kernel<1024, 2>;
+        case 1024 * 16 + 4: return sssp_nearfar_kernel<1024, 4>;
+        case 1024 * 16 + 8: return sssp_nearfar_kernel<1024, 8>;
+    }
+    return nullptr;
+}
+
+struct SsspLaunch {
+    SsspKernel fn = nullptr;
+    int block = 0, grid = 0;
+    size_t smem = 0;
+    u32 scap = 0;
+};
+
+static int plan_sssp(s4_graph *g, SsspLaunch *L)
+{
+    const Options &o = g->ctx->opt;
+    L->fn = pick_sssp(o.block_threads, o.tile);
+    if (!L->fn) return fail(S4_ERR_ARG, "no SSSP kernel for block=%d tile=%d", o.block_threads, o.tile);
+    L->block = o.block_threads;
+    L->scap = (u32)o.near_smem_entries;
+    L->smem = (size_t)2 * L->scap * sizeof(uint2);
+    CU(cudaFuncSetAttribute((const void *)L->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L->smem));
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)L->fn, L->block, L->smem));
+    if (occ < 1) return fail(S4_ERR_ARG, "SSSP kernel does not fit on an SM (block=%d, smem=%zu)", L->block, L->smem);
+    L->grid = g->ctx->prop.multiProcessorCount * std::min(occ, o.ctas_per_sm);
+    return S4_OK;
+}
+
+// pool + per-CTA queue workspace, sized from the options; slots_wanted caps the pool
+static int ensure_scratch(s4_graph *g, const SsspLaunch &L, int64_t slots_wanted)
+{
+    const Options &o = g->ctx->opt;
+    const int64_t V = g->V;
+    int64_t slots = o.batch_roots > 0 ? o.batch_roots : (int64_t)(o.pool_bytes / (8.0 * (double)V));
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    if (g->pool.p) free_b += g->pool.n * sizeof(u64);
+    const int64_t by_mem = (int64_t)((double)free_b * 0.6 / (8.0 * (double)V));
+    slots = std::max<int64_t>(1, std::min(std::min(slots, by_mem), slots_wanted));
+    if (slots > g->pool_slots || !g->pool.p) {
+        CU(g->pool.alloc((size_t)slots * (size_t)V));
+        g->pool_slots = slots;
+    }
+    int64_t q = o.queue_entries > 0 ? o.queue_entries : std::max<int64_t>(65536, V / 4);
+    q = std::min<int64_t>(q, std::max<int64_t>(V, 1024) * 2);
+    if (L.grid > g->ws_ctas || (u32)q != g->near_gcap || !g->ws_near.p) {
+        CU(g->ws_near.alloc((size_t)L.grid * 2 * (size_t)q));
+        CU(g->ws_far.alloc((size_t)L.grid * 2 * (size_t)q));
+        g->ws_ctas = L.grid;
+        g->near_gcap = (u32)q;
+        g->far_cap = (u32)q;
+    }
+    return S4_OK;
+}
+
+static int launch_sssp(s4_graph *g, const SsspLaunch &L, const Arc *arcs, const int32_t *d_roots, int n_roots,
+                       u32 *work_counter, const double *wsum, u64 *counters)
+{
+    SsspParams p;
+    p.row_ptr = g->row_ptr.p;
+    p.arcs = arcs;
+    p.dist_pool = g->pool.p;
+    p.roots = d_roots;
+    p.n_roots = n_roots;
+    p.V = (u32)g->V;
+    p.work_counter = work_counter;
+    p.wsum = wsum;
+    p.delta_scale = g->S > 0 ? g->ctx->opt.delta_factor / (double)g->S : 0.0;
+    p.ws_near = g->ws_near.p;
+    p.ws_far = g->ws_far.p;
+    p.near_scap = L.scap;
+    p.near_gcap = g->near_gcap;
+    p.far_cap = g->far_cap;
+    p.counters = counters;
+    const int grid = std::min(L.grid, std::max(1, n_roots));
+    L.fn<<<grid, L.block, L.smem, g->ctx->stream>>>(p);
+    CU(cudaGetLastError());
+    return S4_OK;
+}
+
+static int launch_pred(s4_graph *g, const Arc *arcs, const u64 *dist, u32 root, int32_t *pred)
+{
+    const int tile = g->ctx->opt.walk_tile;
+    const int block = 256;
+    const int grid = grid_for((int64_t)g->V * tile, block, g->ctx);
+    cudaStream_t st = g->ctx->stream;
+    switch (tile) {
+        case 4: pred_kernel<4><<<grid, block, 0, st>>>(g->row_ptr.p, arcs, dist, (u32)g->V, root, pred); break;
+        case 8: pred_kernel<8><<<grid, block, 0, st>>>(g->row_ptr.p, arcs, dist, (u32)g->V, root, pred); break;
+        case 16: pred_kernel<16><<<grid, block, 0, st>>>(g->row_ptr.p, arcs, dist, (u32)g->V, root, pred); break;
+        default: pred_kernel<32><<<grid, block, 0, st>>>(g->row_ptr.p, arcs, dist, (u32)g->V, root, pred); break;
+    }
+    CU(cudaGetLastError());
+    return S4_OK;
+}
+
+static int launch_walk(s4_graph *g, const WalkParams &p)
+{
+    const int tile = g->ctx->opt.walk_tile;
+    const int block = 256;
+    const int grid = grid_for((p.t1 - p.t0) * tile, block, g->ctx);
+    cudaStream_t st = g->ctx->stream;
+    switch (tile) {
+        case 4: walk_kernel<4><<<grid, block, 0, st>>>(p); break;
+        case 8: walk_kernel<8><<<grid, block, 0, st>>>(p); break;
+        case 16: walk_kernel<16><<<grid, block, 0, st>>>(p); break;
+        default: walk_kernel<32><<<grid, block, 0, st>>>(p); break;
+    }
+    CU(cudaGetLastError());
+    return S4_OK;
+}
+
+extern "C" int s4_graph_sssp(s4_graph *g, const double *w_street, int32_t origin, double *dist_out, int32_t *pred_out)
+{
+    CHECK_ARG(g && w_street, "s4_graph_sssp: NULL argument");
+    CHECK_ARG(origin >= 0 && origin < g->V, "s4_graph_sssp: origin out of range");
+    s4_ctx *ctx = g->ctx;
+    CU(cudaSetDevice(ctx->device));
+    for (int64_t s = 0; s < g->S; ++s)
+        if (!(w_street[s] >= 0.0)) return fail(S4_ERR_ARG, "street %lld: weight must be >= 0", (long long)s);
+    SsspLaunch L;
+    int rc = plan_sssp(g, &L);
+    if (rc) return rc;
+    rc = ensure_scratch(g, L, 1);
+    if (rc) return rc;
+    CU(g->arcs_tmp.ensure((size_t)std::max<int64_t>(g->A, 1)));
+    CU(g->w_tmp.ensure((size_t)std::max<int64_t>(g->S, 1)));
+    CU(g->pred_tmp.ensure((size_t)g->V));
+    CU(g->root_tmp.ensure(1));
+    CU(g->ctr_tmp.ensure(C_COUNT));
+    CU(g->wsum_tmp.ensure(1));
+    CU(g->work_counters.ensure(1024));
+    cudaStream_t st = ctx->stream;
+    double wsum = 0.0;
+    for (int64_t s = 0; s < g->S; ++s) wsum += w_street[s];
+    if (g->S > 0) CU(cudaMemcpyAsync(g->w_tmp.p, w_street, (size_t)g->S * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(g->wsum_tmp.p, &wsum, sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(g->root_tmp.p, &origin, sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(g->ctr_tmp.p, 0, C_COUNT * sizeof(u64), st));
+    CU(cudaMemsetAsync(g->work_counters.p, 0, sizeof(u32), st));
+    if (g->A > 0) {
+        weights_arc_kernel<<<grid_for(g->A, 256, ctx), 256, 0, st>>>(g->A, g->arc_cs.p, g->w_tmp.p, g->arcs_tmp.p);
+        CU(cudaGetLastError());
+    }
+    rc = launch_sssp(g, L, g->arcs_tmp.p, g->root_tmp.p, 1, g->work_counters.p, g->wsum_tmp.p, g->ctr_tmp.p);
+    if (rc) return rc;
+    if (pred_out) {
+        rc = launch_pred(g, g->arcs_tmp.p, g->pool.p, (u32)origin, g->pred_tmp.p);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(pred_out, g->pred_tmp.p, (size_t)g->V * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    }
+    if (dist_out) CU(cudaMemcpyAsync(dist_out, g->pool.p, (size_t)g->V * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return S4_OK;
+}
+
+// ---------------------------------------------------------------------------
+// simulation
+// ---------------------------------------------------------------------------
+static int cub_sort_pairs(s4_ctx *ctx, DevBuf<unsigned char> &tmp, const u32 *kin, u32 *kout, const u32 *vin, u32 *vout, int64_t n)
+{
+    size_t bytes = 0;
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, (int)n, 0, 32, ctx->stream));
+    CU(tmp.ensure(bytes + 16));
+    CU(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, kin, kout, vin, vout, (int)n, 0, 32, ctx->stream));
+    return S4_OK;
+}
+
+// number of distinct values in a host int32 array (used only to resolve S4_ROOT_AUTO)
+static int64_t count_distinct_host(const int32_t *a, int64_t n, int32_t V)
+{
+    std::vector<uint8_t> seen((size_t)V, 0);
+    int64_t d = 0;
+    for (int64_t i = 0; i < n; ++i)
+        if (!seen[(size_t)a[i]]) { seen[(size_t)a[i]] = 1; ++d; }
+    return d;
+}
+
+extern "C" int s4_sim_create(s4_graph *g, int64_t T, const int32_t *origin, const int32_t *goal, double jam_tolerance,
+                             const s4_physics *phys, s4_sim **out)
+{
+    CHECK_ARG(g && out && phys, "s4_sim_create: NULL argument");
+    *out = nullptr;
+    CHECK_ARG(T >= 0 && T < (int64_t)1 << 31, "s4_sim_create: T out of range");
+    CHECK_ARG(T == 0 || (origin && goal), "s4_sim_create: NULL trip array");
+    CHECK_ARG(jam_tolerance == jam_tolerance, "s4_sim_create: jam_tolerance is NaN");
+    s4_ctx *ctx = g->ctx;
+    CU(cudaSetDevice(ctx->device));
+    for (int64_t i = 0; i < T; ++i)
+        if (origin[i] < 0 || origin[i] >= g->V || goal[i] < 0 || goal[i] >= g->V)
+            return fail(S4_ERR_ARG, "trip %lld: node id out of range", (long long)i);
+    s4_sim *sim = new (std::nothrow) s4_sim();
+    if (!sim) return fail(S4_ERR_OOM, "host allocation failed");
+    struct Guard { s4_sim *s; ~Guard() { delete s; } } guard{sim};
+    sim->g = g;
+    sim->T = T;
+    sim->jam = jam_tolerance;
+    sim->ph = Phys{phys->car_length, phys->min_breaking_distance, phys->braking_deceleration};
+    sim->volume = phys->trip_volume;
+    int mode = ctx->opt.root_mode;
+    if (mode == S4_ROOT_AUTO)
+        mode = (T > 0 && count_distinct_host(goal, T, g->V) < count_distinct_host(origin, T, g->V)) ? S4_ROOT_GOAL : S4_ROOT_ORIGIN;
+    sim->root_mode = mode;
+    const int32_t *root_h = mode == S4_ROOT_GOAL ? goal : origin;
+    const int32_t *target_h = mode == S4_ROOT_GOAL ? origin : goal;
+    cudaStream_t st = ctx->stream;
+    const int64_t S = g->S, A = g->A;
+
+    CU(sim->load.alloc((size_t)std::max<int64_t>(S, 1)));
+    CU(sim->cum.alloc((size_t)std::max<int64_t>(S, 1)));
+    CU(sim->ms_vis.alloc((size_t)std::max<int64_t>(S, 1)));
+    CU(sim->ms_ins.alloc((size_t)std::max<int64_t>(S, 1)));
+    CU(sim->w_street.alloc((size_t)std::max<int64_t>(S, 1)));
+    CU(sim->arcs.alloc((size_t)std::max<int64_t>(A, 1)));
+    CU(sim->wsum.alloc(1));
+    CU(sim->counters.alloc(C_COUNT));
+    CU(cudaMemsetAsync(sim->load.p, 0, (size_t)std::max<int64_t>(S, 1) * sizeof(u32), st));   // simulation.py:43
+    CU(cudaMemsetAsync(sim->cum.p, 0, (size_t)std::max<int64_t>(S, 1) * sizeof(u32), st));
+    CU(cudaMemsetAsync(sim->counters.p, 0, C_COUNT * sizeof(u64), st));
+    CU(cudaMemsetAsync(sim->wsum.p, 0, sizeof(double), st));
+    if (S > 0) {
+        CU(cudaMemcpyAsync(sim->ms_vis.p, g->max_speed0.data(), (size_t)S * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(sim->ms_ins.p, g->max_speed0.data(), (size_t)S * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    }
+
+    // ---- group the trips by tree root on the device (tripgenerator.py:37-42)
+    if (T > 0) {
+        DevBuf<u32> kin, kout, vin, vout, flag, rank;
+        DevBuf<int64_t> off;
+        DevBuf<unsigned char> tmp;
+        CU(kin.alloc((size_t)T)); CU(kout.alloc((size_t)T)); CU(vin.alloc((size_t)T)); CU(vout.alloc((size_t)T));
+        CU(flag.alloc((size_t)T)); CU(rank.alloc((size_t)T));
+        CU(cudaMemcpyAsync(kin.p, root_h, (size_t)T * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(vin.p, target_h, (size_t)T * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        int rc = cub_sort_pairs(ctx, tmp, kin.p, kout.p, vin.p, vout.p, T);
+        if (rc) return rc;
+        const int grid = grid_for(T, 256, ctx);
+        head_flag_kernel<<<grid, 256, 0, st>>>(T, (const int32_t *)kout.p, flag.p);
+        CU(cudaGetLastError());
+        size_t bytes = 0;
+        CU(cub::DeviceScan::InclusiveSum(nullptr, bytes, flag.p, rank.p, (int)T, st));
+        CU(tmp.ensure(bytes + 16));
+        CU(cub::DeviceScan::InclusiveSum(tmp.p, bytes, flag.p, rank.p, (int)T, st));
+        u32 D = 0;
+        CU(cudaMemcpyAsync(&D, rank.p + (T - 1), sizeof(u32), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        sim->D = D;
+        CU(sim->roots.alloc((size_t)D));
+        CU(off.alloc((size_t)D + 1));
+        CU(sim->trip_root.alloc((size_t)T));
+        CU(sim->trip_target.alloc((size_t)T));
+        group_scatter_kernel<<<grid, 256, 0, st>>>(T, (const int32_t *)kout.p, flag.p, rank.p, sim->trip_root.p, sim->roots.p, off.p);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(sim->trip_target.p, vout.p, (size_t)T * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+        sim->h_root_off.resize((size_t)D + 1);
+        std::vector<int32_t> h_roots((size_t)D);
+        CU(cudaMemcpyAsync(sim->h_root_off.data(), off.p, (size_t)D * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(h_roots.data(), sim->roots.p, (size_t)D * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        sim->h_root_off[(size_t)D] = T;
+        for (u32 i = 0; i < D; ++i) {
+            const int32_t c = g->comp_of[(size_t)h_roots[i]];
+            sim->alg_arcs_per_day += g->comp_arcs[(size_t)c];
+            sim->alg_nodes_per_day += g->comp_nodes[(size_t)c];
+        }
+    } else {
+        sim->h_root_off.assign(1, 0);
+        CU(cudaStreamSynchronize(st));
+    }
+    guard.s = nullptr;
+    *out = sim;
+    return S4_OK;
+}
+
+static void free_events(std::vector<EvPair> &v)
+{
+    for (auto &e : v) {
+        if (e.a) cudaEventDestroy(e.a);
+        if (e.b) cudaEventDestroy(e.b);
+    }
+    v.clear();
+}
+
+extern "C" int s4_sim_free(s4_sim *sim)
+{
+    if (!sim) return S4_OK;
+    cudaSetDevice(sim->g->ctx->device);
+    cudaStreamSynchronize(sim->g->ctx->stream);
+    free_events(sim->ev_w);
+    free_events(sim->ev_sssp);
+    free_events(sim->ev_walk);
+    free_events(sim->ev_adapt);
+    free_events(sim->ev_step);
+    delete sim;
+    return S4_OK;
+}
+
+extern "C" int s4_sim_roots(s4_sim *sim, int64_t *n_roots, int *root_mode)
+{
+    CHECK_ARG(sim, "s4_sim_roots: sim is NULL");
+    if (n_roots) *n_roots = sim->D;
+    if (root_mode) *root_mode = sim->root_mode;
+    return S4_OK;
+}
+
+// ---- event bookkeeping: pairs are recorded around kernels and harvested lazily
+static int ev_begin(std::vector<EvPair> &v, size_t &used, cudaStream_t st)
+{
+    if (used == v.size()) {
+        EvPair p;
+        CU(cudaEventCreate(&p.a));
+        CU(cudaEventCreate(&p.b));
+        v.push_back(p);
+    }
+    CU(cudaEventRecord(v[used].a, st));
+    return S4_OK;
+}
+static int ev_end(std::vector<EvPair> &v, size_t &used, cudaStream_t st)
+{
+    CU(cudaEventRecord(v[used].b, st));
+    ++used;
+    return S4_OK;
+}
+static int ev_harvest(std::vector<EvPair> &v, size_t &used, double *acc)
+{
+    for (size_t i = 0; i < used; ++i) {
+        CU(cudaEventSynchronize(v[i].b));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, v[i].a, v[i].b));
+        *acc += (double)ms;
+    }
+    used = 0;
+    return S4_OK;
+}
+static int harvest_all(s4_sim *sim)
+{
+    int rc;
+    if ((rc = ev_harvest(sim->ev_w, sim->used_w, &sim->acc.ms_weights))) return rc;
+    if ((rc = ev_harvest(sim->ev_sssp, sim->used_sssp, &sim->acc.ms_sssp))) return rc;
+    if ((rc = ev_harvest(sim->ev_walk, sim->used_walk, &sim->acc.ms_walk))) return rc;
+    if ((rc = ev_harvest(sim->ev_adapt, sim->used_adapt, &sim->acc.ms_adapt))) return rc;
+    if ((rc = ev_harvest(sim->ev_step, sim->used_step, &sim->acc.ms_step_total))) return rc;
+    return S4_OK;
+}
+
+// K1 on the stream: w_street, arc records, sum(w)
+static int run_weights(s4_sim *sim, int reset_load)
+{
+    s4_graph *g = sim->g;
+    s4_ctx *ctx = g->ctx;
+    cudaStream_t st = ctx->stream;
+    CU(cudaMemsetAsync(sim->wsum.p, 0, sizeof(double), st));
+    if (g->S > 0) {
+        weights_street_kernel<<<grid_for(g->S, 256, ctx), 256, 0, st>>>(g->S, g->length.p, sim->ms_vis.p, sim->load.p, sim->jam,
+                                                                        sim->ph, reset_load, sim->w_street.p, sim->wsum.p);
+        CU(cudaGetLastError());
+        ++sim->acc.kernel_launches;
+    }
+    if (g->A > 0) {
+        weights_arc_kernel<<<grid_for(g->A, 256, ctx), 256, 0, st>>>(g->A, g->arc_cs.p, sim->w_street.p, sim->arcs.p);
+        CU(cudaGetLastError());
+        ++sim->acc.kernel_launches;
+    }
+    sim->weights_valid = true;
+    return S4_OK;
+}
+
+extern "C" int s4_sim_weights(s4_sim *sim, int refresh, double *w_out)
+{
+    CHECK_ARG(sim, "s4_sim_weights: sim is NULL");
+    s4_ctx *ctx = sim->g->ctx;
+    CU(cudaSetDevice(ctx->device));
+    if (!refresh && !sim->weights_valid) return fail(S4_ERR_STATE, "s4_sim_weights: no weights computed yet");
+    if (refresh) {
+        int rc = run_weights(sim, 0);
+        if (rc) return rc;
+    }
+    if (w_out && sim->g->S > 0)
+        CU(cudaMemcpyAsync(w_out, sim->w_street.p, (size_t)sim->g->S * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return S4_OK;
+}
+
+extern "C" int s4_sim_step(s4_sim *sim)
+{
+    CHECK_ARG(sim, "s4_sim_step: sim is NULL");
+    s4_graph *g = sim->g;
+    s4_ctx *ctx = g->ctx;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    int rc = harvest_all(sim);          // events of the previous day (already complete in practice)
+    if (rc) return rc;
+    SsspLaunch L;
+    if ((rc = plan_sssp(g, &L))) return rc;
+    if (sim->D > 0 && (rc = ensure_scratch(g, L, sim->D))) return rc;
+
+    if ((rc = ev_begin(sim->ev_step, sim->used_step, st))) return rc;
+    // ---- K1 (simulation.py:53-65) + reset of today's counters (:68)
+    if ((rc = ev_begin(sim->ev_w, sim->used_w, st))) return rc;
+    if ((rc = run_weights(sim, 1))) return rc;
+    if ((rc = ev_end(sim->ev_w, sim->used_w, st))) return rc;
+
+    // ---- K2 + K3 in batches of pool_slots roots (simulation.py:71-88)
+    const int64_t D = sim->D;
+    const int64_t B = std::max<int64_t>(1, g->pool_slots);
+    const int64_t n_batches = (D + B - 1) / B;
+    if (n_batches > 0) {
+        CU(g->work_counters.ensure((size_t)std::max<int64_t>(n_batches, 1024)));
+        CU(cudaMemsetAsync(g->work_counters.p, 0, g->work_counters.n * sizeof(u32), st));
+    }
+    for (int64_t bi = 0; bi < n_batches; ++bi) {
+        const int64_t r0 = bi * B, r1 = std::min(D, r0 + B);
+        if ((rc = ev_begin(sim->ev_sssp, sim->used_sssp, st))) return rc;
+        if ((rc = launch_sssp(g, L, sim->arcs.p, sim->roots.p + r0, (int)(r1 - r0), g->work_counters.p + bi,
+                              sim->wsum.p, sim->counters.p))) return rc;
+        if ((rc = ev_end(sim->ev_sssp, sim->used_sssp, st))) return rc;
+        ++sim->acc.kernel_launches;
+        ++sim->acc.sssp_launches;
+        WalkParams wp;
+        wp.row_ptr = g->row_ptr.p;
+        wp.arcs = sim->arcs.p;
+        wp.dist_pool = g->pool.p;
+        wp.roots = sim->roots.p;
+        wp.trip_target = sim->trip_target.p;
+        wp.trip_root = sim->trip_root.p;
+        wp.t0 = sim->h_root_off[(size_t)r0];
+        wp.t1 = sim->h_root_off[(size_t)r1];
+        wp.root0 = (u32)r0;
+        wp.V = (u32)g->V;
+        wp.volume = sim->volume;
+        wp.load = sim->load.p;
+        wp.counters = sim->counters.p;
+        if ((rc = ev_begin(sim->ev_walk, sim->used_walk, st))) return rc;
+        if ((rc = launch_walk(g, wp))) return rc;
+        if ((rc = ev_end(sim->ev_walk, sim->used_walk, st))) return rc;
+        ++sim->acc.kernel_launches;
+    }
+    if ((rc = ev_end(sim->ev_step, sim->used_step, st))) return rc;
+    sim->acc.days += 1;
+    sim->acc.sssp_instances += (uint64_t)D;
+    sim->acc.arcs_algorithmic += (uint64_t)sim->alg_arcs_per_day;
+    sim->acc.nodes_algorithmic += (uint64_t)sim->alg_nodes_per_day;
+    return S4_OK;
+}
+
+extern "C" int s4_sim_get_load(s4_sim *sim, uint32_t *out)
+{
+    CHECK_ARG(sim && out, "s4_sim_get_load: NULL argument");
+    s4_ctx *ctx = sim->g->ctx;
+    CU(cudaSetDevice(ctx->device));
+    if (sim->g->S > 0) CU(cudaMemcpyAsync(out, sim->load.p, (size_t)sim->g->S * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return S4_OK;
+}
+
+extern "C" int s4_sim_set_load(s4_sim *sim, const uint32_t *in)
+{
+    CHECK_ARG(sim && in, "s4_sim_set_load: NULL argument");
+    s4_ctx *ctx = sim->g->ctx;
+    CU(cudaSetDevice(ctx->device));
+    if (sim->g->S > 0) CU(cudaMemcpyAsync(sim->load.p, in, (size_t)sim->g->S * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));     // the host buffer is only borrowed
+    return S4_OK;
+}
+
+extern "C" void *s4_sim_load_device_ptr(s4_sim *sim) { return sim ? (void *)sim->load.p : nullptr; }
+
+extern "C" int s4_sim_load_add(s4_sim *dst, s4_sim *src)
+{
+    CHECK_ARG(dst && src && dst->g == src->g, "s4_sim_load_add: simulations must share a graph");
+    s4_ctx *ctx = dst->g->ctx;
+    CU(cudaSetDevice(ctx->device));
+    if (dst->g->S > 0 && dst != src) {
+        add_u32_kernel<<<grid_for(dst->g->S, 256, ctx), 256, 0, ctx->stream>>>(dst->g->S, dst->load.p, src->load.p);
+        CU(cudaGetLastError());
+        ++dst->acc.kernel_launches;
+    }
+    return S4_OK;
+}
+
+extern "C" int s4_sim_load_copy(s4_sim *dst, s4_sim *src)
+{
+    CHECK_ARG(dst && src && dst->g == src->g, "s4_sim_load_copy: simulations must share a graph");
+    s4_ctx *ctx = dst->g->ctx;
+    CU(cudaSetDevice(ctx->device));
+    if (dst->g->S > 0 && dst != src)
+        CU(cudaMemcpyAsync(dst->load.p, src->load.p, (size_t)dst->g->S * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->stream));
+    return S4_OK;
+}
+
+extern "C" int s4_sim_commit_total(s4_sim *sim)
+{
+    CHECK_ARG(sim, "s4_sim_commit_total: sim is NULL");
+    s4_ctx *ctx = sim->g->ctx;
+    CU(cudaSetDevice(ctx->device));
+    const int64_t S = sim->g->S;
+    if (S > 0) {
+        if (!sim->has_cum) {
+            // merge_arrays((total, None)) == total   (utils.py:30)
+            CU(cudaMemcpyAsync(sim->cum.p, sim->load.p, (size_t)S * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->stream));
+        } else {
+            add_u32_kernel<<<grid_for(S, 256, ctx), 256, 0, ctx->stream>>>(S, sim->cum.p, sim->load.p);
+            CU(cudaGetLastError());
+            ++sim->acc.kernel_launches;
+        }
+    }
+    sim->has_cum = true;
+    return S4_OK;
+}
+
+extern "C" int s4_sim_get_cumulative(s4_sim *sim, uint32_t *out, int *is_none)
+{
+    CHECK_ARG(sim, "s4_sim_get_cumulative: sim is NULL");
+    s4_ctx *ctx = sim->g->ctx;
+    CU(cudaSetDevice(ctx->device));
+    if (is_none) *is_none = sim->has_cum ? 0 : 1;
+    if (out && sim->has_cum && sim->g->S > 0)
+        CU(cudaMemcpyAsync(out, sim->cum.p, (size_t)sim->g->S * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return S4_OK;
+}
+
+extern "C" int s4_sim_set_cumulative(s4_sim *sim, const uint32_t *in_or_null)
+{
+    CHECK_ARG(sim, "s4_sim_set_cumulative: sim is NULL");
+    s4_ctx *ctx = sim->g->ctx;
+    CU(cudaSetDevice(ctx->device));
+    if (!in_or_null) { sim->has_cum = false; return S4_OK; }
+    if (sim->g->S > 0) CU(cudaMemcpyAsync(sim->cum.p, in_or_null, (size_t)sim->g->S * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    sim->has_cum = true;
+    return S4_OK;
+}
+
+// simulation.py:97-108 control flow, executed literally on the host for n streets
+static void construction_counts(int64_t n, int64_t *n_dec, int64_t *n_inc)
+{
+    double dec_limit = 0.15 * (double)n, inc_limit = 0.95 * (double)n;
+    int64_t nd = 0, ni = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        if ((double)i <= dec_limit) { ++nd; dec_limit += 1.0; }      // :100-102 (`if not None` is always true)
+        const int64_t j = n - i - 1;                                 // :103
+        if ((double)j >= inc_limit) { ++ni; inc_limit -= 1.0; }      // :104-106
+        if (dec_limit >= inc_limit) break;                           // :107
+    }
+    *n_dec = nd;
+    *n_inc = ni;
+}
+
+extern "C" int s4_sim_road_construction(s4_sim *sim, const uint8_t *adaptable)
+{
+    CHECK_ARG(sim, "s4_sim_road_construction: sim is NULL");
+    if (!sim->has_cum) return fail(S4_ERR_STATE, "road_construction: cumulative_traffic_load is None (simulation.py:94 would raise)");
+    s4_graph *g = sim->g;
+    s4_ctx *ctx = g->ctx;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int64_t S = g->S;
+    int rc;
+    if (S > 0) {
+        CU(sim->sort_vals.ensure((size_t)S));
+        CU(sim->sort_keys_out.ensure((size_t)S));
+        CU(sim->order.ensure((size_t)S));
+        if ((rc = ev_begin(sim->ev_adapt, sim->used_adapt, st))) return rc;
+        iota_kernel<<<grid_for(S, 256, ctx), 256, 0, st>>>(S, sim->sort_vals.p);
+        CU(cudaGetLastError());
+        // stable LSD radix sort by load; values start in street_index order => ties keep it (:96)
+        if ((rc = cub_sort_pairs(ctx, sim->cub_tmp, sim->cum.p, sim->sort_keys_out.p, sim->sort_vals.p, sim->order.p, S))) return rc;
+        int64_t n_dec = 0, n_inc = 0;
+        construction_counts(S, &n_dec, &n_inc);
+        const uint8_t *d_mask = nullptr;
+        if (adaptable) {
+            CU(sim->mask.ensure((size_t)S));
+            CU(cudaMemcpyAsync(sim->mask.p, adaptable, (size_t)S, cudaMemcpyHostToDevice, st));
+            d_mask = sim->mask.p;
+        }
+        adapt_kernel<<<grid_for(S, 256, ctx), 256, 0, st>>>(S, sim->order.p, n_dec, n_inc, d_mask, sim->ms_vis.p, sim->ms_ins.p);
+        CU(cudaGetLastError());
+        if ((rc = ev_end(sim->ev_adapt, sim->used_adapt, st))) return rc;
+        sim->acc.kernel_launches += 3;
+        if (adaptable) CU(cudaStreamSynchronize(st));   // borrowed host mask
+    }
+    sim->has_cum = false;                               // simulation.py:109
+    return S4_OK;
+}
+
+extern "C" int s4_sim_get_max_speed(s4_sim *sim, int32_t *visible_out, int32_t *insertion_out)
+{
+    CHECK_ARG(sim, "s4_sim_get_max_speed: sim is NULL");
+    s4_ctx *ctx = sim->g->ctx;
+    CU(cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)sim->g->S * sizeof(int32_t);
+    if (visible_out && bytes) CU(cudaMemcpyAsync(visible_out, sim->ms_vis.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (insertion_out && bytes) CU(cudaMemcpyAsync(insertion_out, sim->ms_ins.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return S4_OK;
+}
+
+extern "C" int s4_sim_set_max_speed(s4_sim *sim, const int32_t *visible, const int32_t *insertion_or_null)
+{
+    CHECK_ARG(sim && visible, "s4_sim_set_max_speed: NULL argument");
+    s4_ctx *ctx = sim->g->ctx;
+    CU(cudaSetDevice(ctx->device));
+    const int64_t S = sim->g->S;
+    for (int64_t s = 0; s < S; ++s)
+        if (visible[s] < 1) return fail(S4_ERR_ARG, "street %lld: max_speed must be >= 1", (long long)s);
+    const size_t bytes = (size_t)S * sizeof(int32_t);
+    if (bytes) {
+        CU(cudaMemcpyAsync(sim->ms_vis.p, visible, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(sim->ms_ins.p, insertion_or_null ? insertion_or_null : visible, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    return S4_OK;
+}
+
+extern "C" int s4_sim_get_counters(s4_sim *sim, s4_counters *out)
+{
+    CHECK_ARG(sim && out, "s4_sim_get_counters: NULL argument");
+    s4_ctx *ctx = sim->g->ctx;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    int rc = harvest_all(sim);
+    if (rc) return rc;
+    u64 h[C_COUNT];
+    CU(cudaMemcpy(h, sim->counters.p, sizeof h, cudaMemcpyDeviceToHost));
+    *out = sim->acc;
+    out->arcs_relaxed = h[C_ARCS_RELAXED];
+    out->nodes_popped = h[C_NODES_POPPED];
+    out->stale_pops = h[C_STALE_POPS];
+    out->queue_pushes = h[C_PUSHES];
+    out->bucket_advances = h[C_ADVANCES];
+    out->relax_rounds = h[C_ROUNDS];
+    out->fallback_sweeps = h[C_FALLBACK_SWEEPS];
+    out->trips_routed = h[C_TRIPS];
+    out->trips_unreachable = h[C_UNREACHABLE];
+    out->trips_stuck = h[C_STUCK];
+    out->hops = h[C_HOPS];
+    return S4_OK;
+}
+
+extern "C" int s4_sim_reset_counters(s4_sim *sim)
+{
+    CHECK_ARG(sim, "s4_sim_reset_counters: sim is NULL");
+    s4_ctx *ctx = sim->g->ctx;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    int rc = harvest_all(sim);
+    if (rc) return rc;
+    CU(cudaMemset(sim->counters.p, 0, C_COUNT * sizeof(u64)));
+    sim->acc = s4_counters{};
+    return S4_OK;
+}
+
+extern "C" int s4_driving_speed(s4_ctx *ctx, int64_t n, const double *length, const int32_t *max_speed,
+                                const uint32_t *trips, const s4_physics *phys, double *out)
+{
+    CHECK_ARG(ctx && phys && n >= 0 && (n == 0 || (length && max_speed && trips && out)), "s4_driving_speed: bad argument");
+    if (n == 0) return S4_OK;
+    CU(cudaSetDevice(ctx->device));
+    DevBuf<double> d_len, d_out;
+    DevBuf<int32_t> d_ms;
+    DevBuf<u32> d_tr;
+    CU(d_len.alloc((size_t)n)); CU(d_out.alloc((size_t)n)); CU(d_ms.alloc((size_t)n)); CU(d_tr.alloc((size_t)n));
+    cudaStream_t st = ctx->stream;
+    CU(cudaMemcpyAsync(d_len.p, length, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_ms.p, max_speed, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_tr.p, trips, (size_t)n * sizeof(u32), cudaMemcpyHostToDevice, st));
+    Phys ph{phys->car_length, phys->min_breaking_distance, phys->braking_deceleration};
+    driving_speed_kernel<<<grid_for(n, 256, ctx), 256, 0, st>>>(n, d_len.p, d_ms.p, d_tr.p, ph, d_out.p);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, d_out.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return S4_OK;
+}

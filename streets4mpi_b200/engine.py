@@ -1,0 +1,243 @@
+"""Object layer over the C-ABI: device context, device-resident street graph and
+per-rank simulation state.  Pure plumbing -- every number is produced by the
+CUDA kernels in ``csrc/``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import Counters, Physics, as_array, check, ptr
+
+_default_device = None
+
+
+class Device(object):
+    """One GPU + one stream (s4_ctx).  ``stream`` is a raw cudaStream_t (int) or
+    None for a library-owned stream."""
+
+    def __init__(self, index=None, stream=None):
+        if index is None:
+            index = int(os.environ.get("LOCAL_RANK", "0"))
+        self.lib = _ffi.load()
+        self.index = int(index)
+        h = C.c_void_p()
+        check(self.lib.s4_ctx_create(self.index, C.c_void_p(stream) if stream else None, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.s4_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        check(self.lib.s4_ctx_sync(self._h))
+
+    def set_option(self, key, value):
+        check(self.lib.s4_ctx_set_option(self._h, key.encode(), float(value)))
+
+    def get_option(self, key):
+        v = C.c_double()
+        check(self.lib.s4_ctx_get_option(self._h, key.encode(), C.byref(v)))
+        return v.value
+
+    def info(self):
+        name = C.create_string_buffer(256)
+        sm = C.c_int()
+        mem = C.c_uint64()
+        check(self.lib.s4_ctx_device_info(self._h, name, 256, C.byref(sm), C.byref(mem)))
+        return {"name": name.value.decode(), "sm_count": sm.value, "hbm_bytes": mem.value}
+
+    def driving_speed(self, length, max_speed, trips, physics):
+        length = as_array(length, np.float64)
+        max_speed = as_array(max_speed, np.int32)
+        trips = as_array(trips, np.uint32)
+        out = np.empty(len(length), dtype=np.float64)
+        check(self.lib.s4_driving_speed(self._h, len(length), ptr(length, C.c_double), ptr(max_speed, C.c_int32),
+                                        ptr(trips, C.c_uint32), C.byref(physics), ptr(out, C.c_double)))
+        return out
+
+
+def default_device():
+    """Process-wide device (cuda:LOCAL_RANK), created on first use."""
+    global _default_device
+    if _default_device is None:
+        _default_device = Device()
+    return _default_device
+
+
+def set_default_device(dev):
+    global _default_device
+    _default_device = dev
+
+
+def make_physics(settings):
+    return Physics(float(settings["car_length"]), float(settings["min_breaking_distance"]),
+                   float(settings["braking_deceleration"]), int(settings["trip_volume"]), 0)
+
+
+class DeviceGraph(object):
+    """Symmetric CSR of the street network in HBM (s4_graph)."""
+
+    def __init__(self, device, V, u, v, length, max_speed):
+        self.device = device
+        self.lib = device.lib
+        u = as_array(u, np.int32)
+        v = as_array(v, np.int32)
+        length = as_array(length, np.float64)
+        max_speed = as_array(max_speed, np.int32)
+        if not (len(u) == len(v) == len(length) == len(max_speed)):
+            raise ValueError("street arrays differ in length")
+        h = C.c_void_p()
+        check(self.lib.s4_graph_upload(device._h, int(V), len(u), ptr(u, C.c_int32), ptr(v, C.c_int32),
+                                       ptr(length, C.c_double), ptr(max_speed, C.c_int32), C.byref(h)))
+        self._h = h
+        self.V, self.S = int(V), len(u)
+        a = C.c_int64()
+        check(self.lib.s4_graph_dims(h, None, None, C.byref(a)))
+        self.A = a.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.s4_graph_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sssp(self, w_street, origin, want_pred=True):
+        """(dist float64[V], pred int32[V]) of one tree."""
+        w = as_array(w_street, np.float64)
+        if len(w) != self.S:
+            raise ValueError("need one weight per street")
+        dist = np.empty(self.V, dtype=np.float64)
+        pred = np.empty(self.V, dtype=np.int32) if want_pred else None
+        check(self.lib.s4_graph_sssp(self._h, ptr(w, C.c_double), int(origin), ptr(dist, C.c_double),
+                                     ptr(pred, C.c_int32) if want_pred else None))
+        return dist, pred
+
+
+class DeviceSim(object):
+    """One (virtual) rank: grouped trips, jam tolerance, load counters (s4_sim)."""
+
+    def __init__(self, graph, origin, goal, jam_tolerance, physics):
+        self.graph = graph
+        self.lib = graph.lib
+        origin = as_array(origin, np.int32)
+        goal = as_array(goal, np.int32)
+        if len(origin) != len(goal):
+            raise ValueError("origin/goal arrays differ in length")
+        h = C.c_void_p()
+        check(self.lib.s4_sim_create(graph._h, len(origin), ptr(origin, C.c_int32), ptr(goal, C.c_int32),
+                                     float(jam_tolerance), C.byref(physics), C.byref(h)))
+        self._h = h
+        self.T = len(origin)
+        n = C.c_int64()
+        m = C.c_int()
+        check(self.lib.s4_sim_roots(h, C.byref(n), C.byref(m)))
+        self.n_roots, self.root_mode = n.value, m.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.s4_sim_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def S(self):
+        return self.graph.S
+
+    def step(self):
+        check(self.lib.s4_sim_step(self._h))
+
+    def weights(self, refresh=False):
+        """Per-street driving times: the ones the last step routed on, or (refresh)
+        recomputed from the resident load."""
+        w = np.empty(self.S, dtype=np.float64)
+        check(self.lib.s4_sim_weights(self._h, 1 if refresh else 0, ptr(w, C.c_double)))
+        return w
+
+    def get_load(self, out=None):
+        if out is None:
+            out = np.empty(self.S, dtype=np.uint32)
+        check(self.lib.s4_sim_get_load(self._h, ptr(out, C.c_uint32)))
+        return out
+
+    def set_load(self, load):
+        load = as_array(load, np.uint32)
+        if len(load) != self.S:
+            raise ValueError("traffic_load must have one entry per street")
+        check(self.lib.s4_sim_set_load(self._h, ptr(load, C.c_uint32)))
+
+    def load_device_ptr(self):
+        return self.lib.s4_sim_load_device_ptr(self._h)
+
+    def load_add(self, other):
+        check(self.lib.s4_sim_load_add(self._h, other._h))
+
+    def load_copy(self, other):
+        check(self.lib.s4_sim_load_copy(self._h, other._h))
+
+    def commit_total(self):
+        check(self.lib.s4_sim_commit_total(self._h))
+
+    def get_cumulative(self):
+        out = np.empty(self.S, dtype=np.uint32)
+        none = C.c_int()
+        check(self.lib.s4_sim_get_cumulative(self._h, ptr(out, C.c_uint32), C.byref(none)))
+        return None if none.value else out
+
+    def set_cumulative(self, cum):
+        if cum is None:
+            check(self.lib.s4_sim_set_cumulative(self._h, None))
+            return
+        cum = as_array(cum, np.uint32)
+        if len(cum) != self.S:
+            raise ValueError("cumulative_traffic_load must have one entry per street")
+        check(self.lib.s4_sim_set_cumulative(self._h, ptr(cum, C.c_uint32)))
+
+    def road_construction(self, adaptable=None):
+        if adaptable is None:
+            check(self.lib.s4_sim_road_construction(self._h, None))
+        else:
+            m = as_array(adaptable, np.uint8)
+            if len(m) != self.S:
+                raise ValueError("adaptable mask must have one entry per street")
+            check(self.lib.s4_sim_road_construction(self._h, ptr(m, C.c_uint8)))
+
+    def get_max_speed(self):
+        vis = np.empty(self.S, dtype=np.int32)
+        ins = np.empty(self.S, dtype=np.int32)
+        check(self.lib.s4_sim_get_max_speed(self._h, ptr(vis, C.c_int32), ptr(ins, C.c_int32)))
+        return vis, ins
+
+    def set_max_speed(self, visible, insertion=None):
+        vis = as_array(visible, np.int32)
+        ins = None if insertion is None else as_array(insertion, np.int32)
+        check(self.lib.s4_sim_set_max_speed(self._h, ptr(vis, C.c_int32),
+                                            None if ins is None else ptr(ins, C.c_int32)))
+
+    def counters(self):
+        c = Counters()
+        check(self.lib.s4_sim_get_counters(self._h, C.byref(c)))
+        return c.as_dict()
+
+    def reset_counters(self):
+        check(self.lib.s4_sim_reset_counters(self._h))

@@ -1,0 +1,106 @@
+"""Seeded synthetic street networks and workloads of the BASELINE shapes.
+
+The reference's own input (osm/test.osm) is a missing blob and there is no
+network, so every configuration runs on generated graphs: 4-neighbour grids
+(cfg3: 1024x1024) and thinned-Delaunay planar road graphs (cfg4/cfg5).  Lengths
+are continuous (ties have probability ~0), speed limits follow a road-class
+mix with a few arterial rows / columns, goals are a small "commercial +
+industrial" node sample and origins are all nodes or a "residential" sample.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .streetnetwork import StreetNetwork
+
+SPEED_CLASSES = np.array([30, 50, 70, 100, 140], dtype=np.int32)
+SPEED_WEIGHTS = np.array([0.45, 0.30, 0.12, 0.08, 0.05])
+
+
+def grid_arrays(rows, cols, seed=1, arterial_every=64):
+    """Street arrays of a rows x cols grid; node id = r * cols + c."""
+    rng = np.random.default_rng(seed)
+    idx = np.arange(rows * cols, dtype=np.int64).reshape(rows, cols)
+    hu, hv = idx[:, :-1].ravel(), idx[:, 1:].ravel()        # horizontal streets
+    vu, vv = idx[:-1, :].ravel(), idx[1:, :].ravel()        # vertical streets
+    u = np.concatenate([hu, vu])
+    v = np.concatenate([hv, vv])
+    S = len(u)
+    length = rng.uniform(20.0, 400.0, size=S)
+    ms = rng.choice(SPEED_CLASSES, size=S, p=SPEED_WEIGHTS).astype(np.int32)
+    if arterial_every:
+        h_row = (hu // cols) % arterial_every == arterial_every // 2
+        v_col = (vu % cols) % arterial_every == arterial_every // 2
+        art = np.concatenate([h_row, v_col])
+        ms[art] = rng.choice(np.array([100, 120, 140], dtype=np.int32), size=int(art.sum()))
+    return {"node_ids": idx.ravel(), "u": u, "v": v, "length": length, "max_speed": ms}
+
+
+def planar_arrays(n_nodes, seed=1, mean_degree=2.4, extent=None):
+    """Random planar road graph: uniform points, Delaunay triangulation thinned to a
+    spanning tree plus the shortest remaining edges up to ``mean_degree`` (real road
+    graphs sit near 2.4).  Euclidean lengths in metres."""
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import minimum_spanning_tree
+    from scipy.spatial import Delaunay
+    rng = np.random.default_rng(seed)
+    extent = extent or 150.0 * np.sqrt(n_nodes)
+    pts = rng.uniform(0.0, extent, size=(n_nodes, 2))
+    tri = Delaunay(pts)
+    e = np.concatenate([tri.simplices[:, [0, 1]], tri.simplices[:, [1, 2]], tri.simplices[:, [0, 2]]])
+    e.sort(axis=1)
+    e = np.unique(e, axis=0)
+    d = np.hypot(*(pts[e[:, 0]] - pts[e[:, 1]]).T)
+    mst = minimum_spanning_tree(coo_matrix((d, (e[:, 0], e[:, 1])), shape=(n_nodes, n_nodes))).tocoo()
+    in_tree = set(zip(mst.row.tolist(), mst.col.tolist()))
+    tree_mask = np.fromiter(((a, b) in in_tree or (b, a) in in_tree for a, b in e.tolist()), dtype=bool, count=len(e))
+    want = int(mean_degree * n_nodes / 2)
+    extra = max(0, want - int(tree_mask.sum()))
+    rest = np.nonzero(~tree_mask)[0]
+    pick = rest[np.argsort(d[rest] * rng.uniform(0.7, 1.3, size=len(rest)))[:extra]]
+    keep = np.concatenate([np.nonzero(tree_mask)[0], pick])
+    keep.sort()
+    u, v, length = e[keep, 0].astype(np.int64), e[keep, 1].astype(np.int64), d[keep]
+    length = np.maximum(length, 1.0)
+    ms = rng.choice(SPEED_CLASSES, size=len(u), p=SPEED_WEIGHTS).astype(np.int32)
+    return {"node_ids": np.arange(n_nodes, dtype=np.int64), "u": u, "v": v, "length": length, "max_speed": ms,
+            "lon": pts[:, 0], "lat": pts[:, 1]}
+
+
+def network_from(arrays):
+    return StreetNetwork.from_arrays(arrays["node_ids"], arrays["u"], arrays["v"], arrays["length"],
+                                     arrays["max_speed"], arrays.get("lon"), arrays.get("lat"))
+
+
+def node_categories(node_ids, seed=1, goal_fraction=0.02, residential_fraction=0.01):
+    """Seeded stand-ins for osmdata's connected_{commercial,industrial,residential}_nodes."""
+    rng = np.random.default_rng(seed + 7919)
+    node_ids = np.asarray(node_ids)
+    n = len(node_ids)
+    n_goal = max(1, int(round(goal_fraction * n)))
+    goals = rng.choice(node_ids, size=n_goal, replace=False)
+    half = n_goal // 2
+    residential = rng.choice(node_ids, size=max(1, int(round(residential_fraction * n))), replace=False)
+    return {"commercial": np.sort(goals[:half]) if half else np.sort(goals), "industrial": np.sort(goals[half:]),
+            "goals": np.sort(goals), "residential": np.sort(residential)}
+
+
+def trip_arrays(n_trips, origins, goals, seed):
+    """Uniform (origin, goal) draws, the array form of tripgenerator.py:33-35."""
+    rng = np.random.default_rng(seed)
+    origins, goals = np.asarray(origins), np.asarray(goals)
+    return origins[rng.integers(0, len(origins), size=n_trips)], goals[rng.integers(0, len(goals), size=n_trips)]
+
+
+def parse_spec(spec):
+    """'synthetic:grid:ROWSxCOLS[:seed]' or 'synthetic:planar:N[:seed]' -> arrays"""
+    parts = spec.split(":")
+    if len(parts) < 3 or parts[0] != "synthetic":
+        raise ValueError("not a synthetic network spec: %r" % (spec,))
+    seed = int(parts[3]) if len(parts) > 3 else 1
+    if parts[1] == "grid":
+        r, c = parts[2].lower().split("x")
+        return grid_arrays(int(r), int(c), seed)
+    if parts[1] == "planar":
+        return planar_arrays(int(parts[2]), seed)
+    raise ValueError("unknown synthetic network kind %r" % (parts[1],))

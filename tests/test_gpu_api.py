@@ -1,0 +1,137 @@
+"""The reference-facing Python API on the GPU: StreetNetwork / Simulation / TripGenerator /
+persistence used the way streets4mpi.py uses them, against the golden fixtures."""
+import os
+from array import array
+
+import numpy as np
+import pytest
+
+from tests.helpers import fh, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _network(case):
+    from streets4mpi_b200 import StreetNetwork
+    net = StreetNetwork()
+    for n in case["nodes"]:
+        net.add_node(n, 0.0, 0.0)
+    for (u, v, L, ms) in case["streets"]:
+        net.add_street((u, v), fh(L), ms)
+    return net
+
+
+def _trips(pairs):
+    d = {}
+    for o, g in pairs:
+        d.setdefault(o, []).append(g)
+    return d
+
+
+def test_reference_driver_protocol_golden():
+    """Exactly the host-array protocol of streets4mpi.py:84-106: step(), read traffic_load,
+    'Allreduce' on the host, assign traffic_load / cumulative_traffic_load back, road_construction."""
+    from streets4mpi_b200 import Simulation, merge_arrays
+    from streets4mpi_b200.settings import settings
+    for case in load_golden("days.json")["cases"]:
+        settings["trip_volume"] = case["trip_volume"]
+        try:
+            sims = [Simulation(_network(case), _trips(t), fh(j), lambda *a: None)
+                    for t, j in zip(case["trips"], case["jams"])]
+            for day, rec in enumerate(case["days"]):
+                if day > 0 and day % case["construction_every"] == 0:
+                    for s in sims:
+                        s.road_construction()
+                        assert s.cumulative_traffic_load is None
+                    seen = dict((idx, ms) for (_st, idx, _l, ms) in sims[0].street_network)
+                    assert [seen[i] for i in range(len(seen))] == rec["max_speed_after_construction"]
+                for s in sims:
+                    s.step()
+                for r, s in enumerate(sims):
+                    assert isinstance(s.traffic_load, array) and s.traffic_load.typecode == "I"
+                    assert list(s.traffic_load) == rec["local_loads"][r], (case["name"], day, r)
+                total = merge_arrays([s.traffic_load for s in sims])
+                for s in sims:
+                    s.traffic_load = total
+                    s.cumulative_traffic_load = merge_arrays((total, s.cumulative_traffic_load))
+                assert list(total) == rec["total"]
+                assert list(sims[0].cumulative_traffic_load) == rec["cumulative"]
+            sims[0].sync_street_network()
+            net = sims[0].street_network
+            w = dict((idx, net.get_driving_time(st)) for (st, idx, _l, _ms) in net)
+            assert [float(w[i]).hex() for i in range(len(w))] == case["days"][-1]["weights"][0]
+        finally:
+            settings["trip_volume"] = 1
+
+
+def test_device_resident_exchange_matches_golden():
+    """Same days through Simulation.exchange(): loads never leave the GPU between days."""
+    from streets4mpi_b200 import Simulation
+    case = [c for c in load_golden("days.json")["cases"] if c["name"] == "grid12x12_3ranks"][0]
+    sims = [Simulation(_network(case), _trips(t), fh(j), lambda *a: None) for t, j in zip(case["trips"], case["jams"])]
+    for day, rec in enumerate(case["days"]):
+        if day > 0 and day % case["construction_every"] == 0:
+            for s in sims:
+                s.road_construction()
+        for s in sims:
+            s.step()
+        sims[0].exchange(virtual_ranks=sims[1:])
+        for s in sims:
+            assert list(s.traffic_load) == rec["total"]
+            assert list(s.cumulative_traffic_load) == rec["cumulative"]
+
+
+def test_three_node_fixture_and_shortest_paths():
+    """simulation.py:147-155, the only fixture the reference ships (with float lengths)."""
+    from streets4mpi_b200 import Simulation, StreetNetwork
+    net = StreetNetwork()
+    for n in (1, 2, 3):
+        net.add_node(n, 0, 0)
+    net.add_street((1, 2), 10.0, 50)
+    net.add_street((2, 3), 100.0, 140)
+    logged = []
+    sim = Simulation(net, {1: [3]}, 0.3, lambda *a: logged.append(a))
+    for _ in range(10):
+        sim.step()
+        assert list(sim.traffic_load) == [1, 1]
+        sim.exchange()
+    assert sim.step_counter == 10 and logged
+    sim.sync_street_network()
+    assert float(net.get_driving_time((1, 2))).hex() == "0x1.2bd4ad642ee50p-2"
+    assert float(net.get_driving_time((3, 2))).hex() == "0x1.76c9d8bd3a9e4p-1"
+    paths = net.calculate_shortest_paths(1)
+    assert paths == {1: None, 2: 1, 3: 2}
+    net.add_node(9, 0, 0)                                  # unreachable node is absent from the result
+    assert 9 not in net.calculate_shortest_paths(1)
+
+
+def test_calculate_driving_speed_function():
+    from streets4mpi_b200 import calculate_driving_speed
+    assert calculate_driving_speed(100.0, 50, 10) == 34.1525987298185
+    assert calculate_driving_speed(3.0, 30, 0) == 0.440908153700972
+    assert calculate_driving_speed(250.0, 140, 0) == 140
+
+
+def test_streets4mpi_driver_end_to_end(tmp_path):
+    """The zero-argument driver on a synthetic network, persisting .s4mpi files."""
+    from streets4mpi_b200 import persistence
+    from streets4mpi_b200.settings import settings
+    from streets4mpi_b200.streets4mpi import Streets4MPI
+    old = dict(settings)
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        settings.update({"osm_file": "synthetic:grid:24x24:3", "logging": None, "max_simulation_steps": 5,
+                         "number_of_residents": 300, "steps_between_street_construction": 2})
+        app = Streets4MPI()
+        files = sorted(os.listdir(tmp_path))
+        assert [f for f in files if f.startswith("traffic_load_")] == ["traffic_load_%d.s4mpi" % i for i in range(1, 6)]
+        assert "street_network_1.s4mpi" in files and "street_network_3.s4mpi" in files and "street_network_5.s4mpi" in files
+        day5 = persistence.persist_read("traffic_load_5.s4mpi", is_array=True)
+        assert list(day5) == list(app.simulation.traffic_load) and sum(day5) > 0
+        net = persistence.persist_read("street_network_5.s4mpi")
+        assert net.street_index == 2 * 24 * 23
+    finally:
+        os.chdir(cwd)
+        settings.clear()
+        settings.update(old)

