@@ -63,7 +63,10 @@ struct Options {
     int walk_tile = 8;
 };
 
+// Lifetime: handles are reference counted (sim -> graph -> ctx), so the host may
+// release them in any order (Python finalisers run in arbitrary order).
 struct s4_ctx {
+    int refs = 1;
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
@@ -97,6 +100,7 @@ struct EvPair {
 };
 
 struct s4_graph {
+    int refs = 1;
     s4_ctx *ctx = nullptr;
     int32_t V = 0;
     int64_t S = 0, A = 0;
@@ -193,12 +197,18 @@ extern "C" int s4_ctx_create(int device, void *stream, s4_ctx **out)
     return S4_OK;
 }
 
-extern "C" int s4_ctx_destroy(s4_ctx *ctx)
+static void ctx_unref(s4_ctx *ctx)
 {
-    if (!ctx) return S4_OK;
+    if (--ctx->refs > 0) return;
     cudaSetDevice(ctx->device);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
+}
+
+extern "C" int s4_ctx_destroy(s4_ctx *ctx)
+{
+    if (!ctx) return S4_OK;
+    ctx_unref(ctx);
     return S4_OK;
 }
 
@@ -316,6 +326,7 @@ extern "C" int s4_graph_upload(s4_ctx *ctx, int32_t V, int64_t S, const int32_t 
     s4_graph *g = new (std::nothrow) s4_graph();
     if (!g) return fail(S4_ERR_OOM, "host allocation failed");
     g->ctx = ctx;
+    ++ctx->refs;
     g->V = V;
     g->S = S;
     g->A = A;
@@ -341,6 +352,7 @@ extern "C" int s4_graph_upload(s4_ctx *ctx, int32_t V, int64_t S, const int32_t 
     }
     auto bail = [&](cudaError_t e, const char *what) {
         delete g;
+        --ctx->refs;
         return fail(e == cudaErrorMemoryAllocation ? S4_ERR_OOM : S4_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
     };
     cudaError_t e;
@@ -355,12 +367,20 @@ extern "C" int s4_graph_upload(s4_ctx *ctx, int32_t V, int64_t S, const int32_t 
     return S4_OK;
 }
 
+static void graph_unref(s4_graph *g)
+{
+    if (--g->refs > 0) return;
+    s4_ctx *ctx = g->ctx;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    delete g;
+    ctx_unref(ctx);
+}
+
 extern "C" int s4_graph_free(s4_graph *g)
 {
     if (!g) return S4_OK;
-    cudaSetDevice(g->ctx->device);
-    cudaStreamSynchronize(g->ctx->stream);
-    delete g;
+    graph_unref(g);
     return S4_OK;
 }
 
@@ -659,6 +679,7 @@ extern "C" int s4_sim_create(s4_graph *g, int64_t T, const int32_t *origin, cons
         CU(cudaStreamSynchronize(st));
     }
     guard.s = nullptr;
+    ++g->refs;
     *out = sim;
     return S4_OK;
 }
@@ -682,7 +703,9 @@ extern "C" int s4_sim_free(s4_sim *sim)
     free_events(sim->ev_walk);
     free_events(sim->ev_adapt);
     free_events(sim->ev_step);
+    s4_graph *g = sim->g;
     delete sim;
+    graph_unref(g);
     return S4_OK;
 }
 
@@ -858,7 +881,7 @@ extern "C" void *s4_sim_load_device_ptr(s4_sim *sim) { return sim ? (void *)sim-
 
 extern "C" int s4_sim_load_add(s4_sim *dst, s4_sim *src)
 {
-    CHECK_ARG(dst && src && dst->g == src->g, "s4_sim_load_add: simulations must share a graph");
+    CHECK_ARG(dst && src && dst->g->ctx == src->g->ctx && dst->g->S == src->g->S, "s4_sim_load_add: simulations must live on one device and have equally many streets");
     s4_ctx *ctx = dst->g->ctx;
     CU(cudaSetDevice(ctx->device));
     if (dst->g->S > 0 && dst != src) {
@@ -871,7 +894,7 @@ extern "C" int s4_sim_load_add(s4_sim *dst, s4_sim *src)
 
 extern "C" int s4_sim_load_copy(s4_sim *dst, s4_sim *src)
 {
-    CHECK_ARG(dst && src && dst->g == src->g, "s4_sim_load_copy: simulations must share a graph");
+    CHECK_ARG(dst && src && dst->g->ctx == src->g->ctx && dst->g->S == src->g->S, "s4_sim_load_copy: simulations must live on one device and have equally many streets");
     s4_ctx *ctx = dst->g->ctx;
     CU(cudaSetDevice(ctx->device));
     if (dst->g->S > 0 && dst != src)

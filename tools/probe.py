@@ -1,0 +1,63 @@
+"""Tuning probe: time a sample of trees on a BASELINE-shaped graph for several kernel options."""
+import argparse
+import json
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, ".")
+from streets4mpi_b200 import engine, synth  # noqa: E402
+from streets4mpi_b200.settings import settings  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--rows", type=int, default=1024)
+ap.add_argument("--cols", type=int, default=1024)
+ap.add_argument("--planar", type=int, default=0)
+ap.add_argument("--roots", type=int, default=1184)
+ap.add_argument("--configs", type=str, default="")
+ap.add_argument("--days", type=int, default=2)
+args = ap.parse_args()
+
+dev = engine.default_device()
+arr = synth.planar_arrays(args.planar, seed=1) if args.planar else synth.grid_arrays(args.rows, args.cols, seed=1)
+V = len(arr["node_ids"])
+cats = synth.node_categories(arr["node_ids"], seed=1)
+rng = np.random.default_rng(0)
+origins = rng.choice(arr["node_ids"], size=args.roots, replace=False)
+goals = cats["goals"][rng.integers(0, len(cats["goals"]), size=args.roots)]
+phys = engine.make_physics(settings)
+g = engine.DeviceGraph(dev, V, arr["u"], arr["v"], arr["length"], arr["max_speed"])
+print("graph V=%d S=%d A=%d" % (V, g.S, g.A), flush=True)
+configs = [dict()]
+if args.configs:
+    configs = [dict((k, float(v)) for k, v in (kv.split("=") for kv in c.split(","))) if c else dict()
+               for c in args.configs.split(";")]
+for cfg in configs:
+    base = {k: dev.get_option(k) for k in cfg}
+    for k, v in cfg.items():
+        dev.set_option(k, v)
+    sim = engine.DeviceSim(g, origins.astype(np.int32), goals.astype(np.int32), 0.4, phys)
+    for d in range(args.days):
+        sim.reset_counters()
+        t0 = time.time()
+        sim.step()
+        dev.sync()
+        wall = time.time() - t0
+        c = sim.counters()
+        sim.commit_total()
+    alg_bytes = 20.0 * c["arcs_algorithmic"] + 20.0 * c["nodes_algorithmic"]
+    out = dict(cfg=cfg, roots=sim.n_roots, ms_sssp=round(c["ms_sssp"], 2), ms_walk=round(c["ms_walk"], 2),
+               ms_w=round(c["ms_weights"], 3), wall_ms=round(wall * 1e3, 1),
+               us_per_tree=round(1e3 * c["ms_sssp"] / sim.n_roots, 1),
+               gteps=round(c["arcs_algorithmic"] / c["ms_sssp"] / 1e6, 2),
+               hbm_frac=round(alg_bytes / (c["ms_sssp"] * 1e-3) / 6540.5e9, 4),
+               relax_x=round(c["arcs_relaxed"] / max(1, c["arcs_algorithmic"]), 2),
+               pops_x=round(c["nodes_popped"] / max(1, c["nodes_algorithmic"]), 2),
+               stale_x=round(c["stale_pops"] / max(1, c["nodes_algorithmic"]), 2),
+               rounds=c["relax_rounds"] // sim.n_roots, adv=c["bucket_advances"] // sim.n_roots,
+               fb=c["fallback_sweeps"], hops=c["hops"])
+    print(json.dumps(out), flush=True)
+    sim.close()
+    for k, v in base.items():
+        dev.set_option(k, v)
