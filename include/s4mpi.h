@@ -95,9 +95,9 @@ int s4_ctx_create(int device, void *stream, s4_ctx **out);
 int s4_ctx_destroy(s4_ctx *ctx);
 int s4_ctx_sync(s4_ctx *ctx);
 /* Tunables (all have defaults): "delta_factor" (bucket width in mean arc
- * weights), "block_threads" (256|512|1024), "tile" (lanes per frontier node:
- * 2|4|8), "ctas_per_sm", "near_smem_entries", "queue_entries", "batch_roots",
- * "pool_bytes", "root_mode" (S4_ROOT_*), "walk_tile" (4|8|16|32). */
+ * weights), "block_threads" (256|512|1024), "ctas_per_sm", "near_smem_entries", "queue_entries", "batch_roots",
+ * "pool_bytes", "root_mode" (S4_ROOT_*), "walk_tile" (4|8|16|32),
+ * "sssp_variant" (0 = barrier per relaxation round, 1 = barrier-free ring). */
 int s4_ctx_set_option(s4_ctx *ctx, const char *key, double value);
 int s4_ctx_get_option(s4_ctx *ctx, const char *key, double *value);
 /* name, SM count, bytes of HBM; name_out may be NULL */

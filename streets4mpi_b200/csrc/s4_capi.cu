@@ -53,7 +53,6 @@ static int fail(int code, const char *fmt, ...)
 struct Options {
     double delta_factor = 2.0;
     int block_threads = 512;
-    int tile = 4;
     int ctas_per_sm = 2;
     int near_smem_entries = 4096;
     int64_t queue_entries = 0;      // 0 = auto (from V)
@@ -61,6 +60,7 @@ struct Options {
     double pool_bytes = 24.0e9;
     int root_mode = S4_ROOT_ORIGIN;
     int walk_tile = 8;
+    int sssp_variant = 1;           // 0 = barrier per relaxation round, 1 = barrier-free ring
 };
 
 // Lifetime: handles are reference counted (sim -> graph -> ctx), so the host may
@@ -106,6 +106,7 @@ struct s4_graph {
     int64_t S = 0, A = 0;
     DevBuf<u32> row_ptr;       // V+1
     DevBuf<uint2> arc_cs;      // A  {head, street}
+    DevBuf<uint2> ell_cs;      // V*4 {head | overflow flag, street}; padding {self, ~0}
     DevBuf<double> length;     // S
     std::vector<int32_t> max_speed0;   // host copy of the uploaded limits
     // connected components (host): algorithmic arcs / nodes of a tree rooted at r
@@ -114,12 +115,13 @@ struct s4_graph {
     // scratch shared by every simulation on this graph (sized lazily)
     DevBuf<u64> pool;          // slots * V
     int64_t pool_slots = 0;
-    DevBuf<uint2> ws_near, ws_far;
+    DevBuf<u32> ws_v;          // per-CTA frontier workspace (nodes / distances)
+    DevBuf<u64> ws_d;
     int ws_ctas = 0;
     u32 near_gcap = 0, far_cap = 0;
     DevBuf<u32> work_counters;
     // single-source API scratch
-    DevBuf<Arc> arcs_tmp;
+    DevBuf<Arc> arcs_tmp, ell_tmp;
     DevBuf<double> w_tmp;
     DevBuf<int32_t> pred_tmp;
     DevBuf<int32_t> root_tmp;
@@ -143,7 +145,8 @@ struct s4_sim {
     bool has_cum = false;
     DevBuf<int32_t> ms_vis, ms_ins;
     DevBuf<double> w_street;
-    DevBuf<Arc> arcs;
+    DevBuf<Arc> arcs;              // CSR records (walk, overflow arcs)
+    DevBuf<Arc> ell;               // fixed-stride records (SSSP)
     DevBuf<double> wsum;
     DevBuf<u64> counters;
     bool weights_valid = false;
@@ -226,10 +229,11 @@ static void option_slot(Options &o, const char *key, int *kind, void **raw)
     struct Item { const char *k; int kind; void *p; };
     Item items[] = {
         {"delta_factor", 0, &o.delta_factor},       {"block_threads", 1, &o.block_threads},
-        {"tile", 1, &o.tile},                       {"ctas_per_sm", 1, &o.ctas_per_sm},
+        {"ctas_per_sm", 1, &o.ctas_per_sm},
         {"near_smem_entries", 1, &o.near_smem_entries}, {"queue_entries", 2, &o.queue_entries},
         {"batch_roots", 2, &o.batch_roots},         {"pool_bytes", 0, &o.pool_bytes},
         {"root_mode", 1, &o.root_mode},             {"walk_tile", 1, &o.walk_tile},
+        {"sssp_variant", 1, &o.sssp_variant},
     };
     for (auto &it : items)
         if (strcmp(it.k, key) == 0) { *kind = it.kind; *raw = it.p; return; }
@@ -250,10 +254,11 @@ extern "C" int s4_ctx_set_option(s4_ctx *ctx, const char *key, double value)
     else *(int64_t *)raw = (int64_t)value;
     const Options &t = trial;
     bool ok = t.delta_factor >= 0.0 && (t.block_threads == 256 || t.block_threads == 512 || t.block_threads == 1024) &&
-              (t.tile == 2 || t.tile == 4 || t.tile == 8) && t.ctas_per_sm >= 1 && t.ctas_per_sm <= 8 &&
-              t.near_smem_entries >= 64 && t.near_smem_entries <= 13000 && t.queue_entries >= 0 &&
+              t.ctas_per_sm >= 1 && t.ctas_per_sm <= 8 &&
+              t.near_smem_entries >= 64 && t.near_smem_entries <= 9000 && t.queue_entries >= 0 &&
               t.batch_roots >= 0 && t.pool_bytes >= 0.0 && t.root_mode >= 0 && t.root_mode <= 2 &&
-              (t.walk_tile == 4 || t.walk_tile == 8 || t.walk_tile == 16 || t.walk_tile == 32);
+              (t.walk_tile == 4 || t.walk_tile == 8 || t.walk_tile == 16 || t.walk_tile == 32) &&
+              (t.sssp_variant == 0 || t.sssp_variant == 1);
     if (!ok) return fail(S4_ERR_ARG, "option '%s': value %g out of range", key, value);
     ctx->opt = trial;
     return S4_OK;
@@ -323,6 +328,14 @@ extern "C" int s4_graph_upload(s4_ctx *ctx, int32_t V, int64_t S, const int32_t 
             if (u[s] != v[s]) arc_cs[fill[(size_t)v[s]]++] = make_uint2((u32)u[s], (u32)s);
         }
     }
+    // fixed-stride table for the SSSP kernel: first kEllWidth arcs of every row
+    std::vector<uint2> ell_cs((size_t)V * kEllWidth);
+    for (int32_t n = 0; n < V; ++n) {
+        const u32 rb = row_ptr[(size_t)n], deg = row_ptr[(size_t)n + 1] - rb;
+        for (u32 k = 0; k < (u32)kEllWidth; ++k)
+            ell_cs[(size_t)n * kEllWidth + k] = k < deg ? arc_cs[rb + k] : make_uint2((u32)n, 0xFFFFFFFFu);
+        if (deg > (u32)kEllWidth) ell_cs[(size_t)n * kEllWidth].x |= kOvfBit;
+    }
     s4_graph *g = new (std::nothrow) s4_graph();
     if (!g) return fail(S4_ERR_OOM, "host allocation failed");
     g->ctx = ctx;
@@ -359,6 +372,8 @@ extern "C" int s4_graph_upload(s4_ctx *ctx, int32_t V, int64_t S, const int32_t 
     if ((e = g->row_ptr.alloc((size_t)V + 1)) != cudaSuccess) return bail(e, "alloc row_ptr");
     if ((e = g->arc_cs.alloc((size_t)std::max<int64_t>(A, 1))) != cudaSuccess) return bail(e, "alloc arcs");
     if ((e = g->length.alloc((size_t)std::max<int64_t>(S, 1))) != cudaSuccess) return bail(e, "alloc length");
+    if ((e = g->ell_cs.alloc((size_t)V * kEllWidth)) != cudaSuccess) return bail(e, "alloc ell");
+    if ((e = cudaMemcpyAsync(g->ell_cs.p, ell_cs.data(), (size_t)V * kEllWidth * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) return bail(e, "copy ell");
     if ((e = cudaMemcpyAsync(g->row_ptr.p, row_ptr.data(), ((size_t)V + 1) * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) return bail(e, "copy row_ptr");
     if (A > 0 && (e = cudaMemcpyAsync(g->arc_cs.p, arc_cs.data(), (size_t)A * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) return bail(e, "copy arcs");
     if (S > 0 && (e = cudaMemcpyAsync(g->length.p, length, (size_t)S * sizeof(double), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) return bail(e, "copy length");
@@ -398,18 +413,12 @@ extern "C" int s4_graph_dims(s4_graph *g, int32_t *V, int64_t *S, int64_t *A)
 // ---------------------------------------------------------------------------
 typedef void (*SsspKernel)(SsspParams);
 
-static SsspKernel pick_sssp(int block, int tile)
+static SsspKernel pick_sssp(int block, int variant)
 {
-    switch (block * 16 + tile) {
-        case 256 * 16 + 2: return sssp_nearfar_kernel<256, 2>;
-        case 256 * 16 + 4: return sssp_nearfar_kernel<256, 4>;
-        case 256 * 16 + 8: return sssp_nearfar_kernel<256, 8>;
-        case 512 * 16 + 2: return sssp_nearfar_kernel<512, 2>;
-        case 512 * 16 + 4: return sssp_nearfar_kernel<512, 4>;
-        case 512 * 16 + 8: return sssp_nearfar_kernel<512, 8>;
-        case 1024 * 16 + 2: return sssp_nearfar_kernel<1024, 2>;
-        case 1024 * 16 + 4: return sssp_nearfar_kernel<1024, 4>;
-        case 1024 * 16 + 8: return sssp_nearfar_kernel<1024, 8>;
+    switch (block) {
+        case 256: return variant ? sssp_async_kernel<256> : sssp_nearfar_kernel<256>;
+        case 512: return variant ? sssp_async_kernel<512> : sssp_nearfar_kernel<512>;
+        case 1024: return variant ? sssp_async_kernel<1024> : sssp_nearfar_kernel<1024>;
     }
     return nullptr;
 }
@@ -424,11 +433,21 @@ struct SsspLaunch {
 static int plan_sssp(s4_graph *g, SsspLaunch *L)
 {
     const Options &o = g->ctx->opt;
-    L->fn = pick_sssp(o.block_threads, o.tile);
-    if (!L->fn) return fail(S4_ERR_ARG, "no SSSP kernel for block=%d tile=%d", o.block_threads, o.tile);
+    L->fn = pick_sssp(o.block_threads, o.sssp_variant);
+    if (!L->fn) return fail(S4_ERR_ARG, "no SSSP kernel for block=%d", o.block_threads);
     L->block = o.block_threads;
-    L->scap = (u32)o.near_smem_entries;
-    L->smem = (size_t)2 * L->scap * sizeof(uint2);
+    if (o.sssp_variant) {
+        // one ring of 2 * near_smem_entries slots rounded down to a power of two (same shared-memory budget),
+        // never smaller than twice the worst-case concurrent push of the CTA
+        u32 want = (u32)o.near_smem_entries * 2u, rcap = 1u;
+        while (rcap * 2u <= want) rcap *= 2u;
+        while (rcap < (u32)o.block_threads * kEllWidth * 2u) rcap *= 2u;
+        L->scap = rcap;
+        L->smem = (size_t)rcap * (sizeof(u64) + sizeof(u32));
+    } else {
+        L->scap = (u32)o.near_smem_entries;
+        L->smem = (size_t)2 * L->scap * (sizeof(u64) + sizeof(u32));
+    }
     CU(cudaFuncSetAttribute((const void *)L->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L->smem));
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)L->fn, L->block, L->smem));
@@ -454,9 +473,9 @@ static int ensure_scratch(s4_graph *g, const SsspLaunch &L, int64_t slots_wanted
     }
     int64_t q = o.queue_entries > 0 ? o.queue_entries : std::max<int64_t>(65536, V / 4);
     q = std::min<int64_t>(q, std::max<int64_t>(V, 1024) * 2);
-    if (L.grid > g->ws_ctas || (u32)q != g->near_gcap || !g->ws_near.p) {
-        CU(g->ws_near.alloc((size_t)L.grid * 2 * (size_t)q));
-        CU(g->ws_far.alloc((size_t)L.grid * 2 * (size_t)q));
+    if (L.grid > g->ws_ctas || (u32)q != g->near_gcap || !g->ws_v.p) {
+        CU(g->ws_v.alloc((size_t)L.grid * 4 * (size_t)q));
+        CU(g->ws_d.alloc((size_t)L.grid * 4 * (size_t)q));
         g->ws_ctas = L.grid;
         g->near_gcap = (u32)q;
         g->far_cap = (u32)q;
@@ -464,10 +483,11 @@ static int ensure_scratch(s4_graph *g, const SsspLaunch &L, int64_t slots_wanted
     return S4_OK;
 }
 
-static int launch_sssp(s4_graph *g, const SsspLaunch &L, const Arc *arcs, const int32_t *d_roots, int n_roots,
-                       u32 *work_counter, const double *wsum, u64 *counters)
+static int launch_sssp(s4_graph *g, const SsspLaunch &L, const Arc *ell, const Arc *arcs, const int32_t *d_roots,
+                       int n_roots, u32 *work_counter, const double *wsum, u64 *counters)
 {
     SsspParams p;
+    p.ell = ell;
     p.row_ptr = g->row_ptr.p;
     p.arcs = arcs;
     p.dist_pool = g->pool.p;
@@ -477,8 +497,8 @@ static int launch_sssp(s4_graph *g, const SsspLaunch &L, const Arc *arcs, const 
     p.work_counter = work_counter;
     p.wsum = wsum;
     p.delta_scale = g->S > 0 ? g->ctx->opt.delta_factor / (double)g->S : 0.0;
-    p.ws_near = g->ws_near.p;
-    p.ws_far = g->ws_far.p;
+    p.ws_v = g->ws_v.p;
+    p.ws_d = g->ws_d.p;
     p.near_scap = L.scap;
     p.near_gcap = g->near_gcap;
     p.far_cap = g->far_cap;
@@ -535,6 +555,7 @@ extern "C" int s4_graph_sssp(s4_graph *g, const double *w_street, int32_t origin
     rc = ensure_scratch(g, L, 1);
     if (rc) return rc;
     CU(g->arcs_tmp.ensure((size_t)std::max<int64_t>(g->A, 1)));
+    CU(g->ell_tmp.ensure((size_t)g->V * kEllWidth));
     CU(g->w_tmp.ensure((size_t)std::max<int64_t>(g->S, 1)));
     CU(g->pred_tmp.ensure((size_t)g->V));
     CU(g->root_tmp.ensure(1));
@@ -553,7 +574,10 @@ extern "C" int s4_graph_sssp(s4_graph *g, const double *w_street, int32_t origin
         weights_arc_kernel<<<grid_for(g->A, 256, ctx), 256, 0, st>>>(g->A, g->arc_cs.p, g->w_tmp.p, g->arcs_tmp.p);
         CU(cudaGetLastError());
     }
-    rc = launch_sssp(g, L, g->arcs_tmp.p, g->root_tmp.p, 1, g->work_counters.p, g->wsum_tmp.p, g->ctr_tmp.p);
+    weights_ell_kernel<<<grid_for((int64_t)g->V * kEllWidth, 256, ctx), 256, 0, st>>>((int64_t)g->V * kEllWidth, g->ell_cs.p,
+                                                                                     g->w_tmp.p, g->ell_tmp.p);
+    CU(cudaGetLastError());
+    rc = launch_sssp(g, L, g->ell_tmp.p, g->arcs_tmp.p, g->root_tmp.p, 1, g->work_counters.p, g->wsum_tmp.p, g->ctr_tmp.p);
     if (rc) return rc;
     if (pred_out) {
         rc = launch_pred(g, g->arcs_tmp.p, g->pool.p, (u32)origin, g->pred_tmp.p);
@@ -623,6 +647,7 @@ extern "C" int s4_sim_create(s4_graph *g, int64_t T, const int32_t *origin, cons
     CU(sim->ms_ins.alloc((size_t)std::max<int64_t>(S, 1)));
     CU(sim->w_street.alloc((size_t)std::max<int64_t>(S, 1)));
     CU(sim->arcs.alloc((size_t)std::max<int64_t>(A, 1)));
+    CU(sim->ell.alloc((size_t)g->V * kEllWidth));
     CU(sim->wsum.alloc(1));
     CU(sim->counters.alloc(C_COUNT));
     CU(cudaMemsetAsync(sim->load.p, 0, (size_t)std::max<int64_t>(S, 1) * sizeof(u32), st));   // simulation.py:43
@@ -775,6 +800,10 @@ static int run_weights(s4_sim *sim, int reset_load)
         CU(cudaGetLastError());
         ++sim->acc.kernel_launches;
     }
+    weights_ell_kernel<<<grid_for((int64_t)g->V * kEllWidth, 256, ctx), 256, 0, st>>>((int64_t)g->V * kEllWidth, g->ell_cs.p,
+                                                                                     sim->w_street.p, sim->ell.p);
+    CU(cudaGetLastError());
+    ++sim->acc.kernel_launches;
     sim->weights_valid = true;
     return S4_OK;
 }
@@ -825,7 +854,7 @@ extern "C" int s4_sim_step(s4_sim *sim)
     for (int64_t bi = 0; bi < n_batches; ++bi) {
         const int64_t r0 = bi * B, r1 = std::min(D, r0 + B);
         if ((rc = ev_begin(sim->ev_sssp, sim->used_sssp, st))) return rc;
-        if ((rc = launch_sssp(g, L, sim->arcs.p, sim->roots.p + r0, (int)(r1 - r0), g->work_counters.p + bi,
+        if ((rc = launch_sssp(g, L, sim->ell.p, sim->arcs.p, sim->roots.p + r0, (int)(r1 - r0), g->work_counters.p + bi,
                               sim->wsum.p, sim->counters.p))) return rc;
         if ((rc = ev_end(sim->ev_sssp, sim->used_sssp, st))) return rc;
         ++sim->acc.kernel_launches;

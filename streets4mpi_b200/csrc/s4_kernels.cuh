@@ -131,6 +131,20 @@ __global__ void weights_arc_kernel(int64_t A, const uint2 *__restrict__ arc_cs, 
     }
 }
 
+// per ELL slot: {head | overflow flag, street, w[street]}; padding slots carry street = ~0 and get w = +inf
+__global__ void weights_ell_kernel(int64_t n_slots, const uint2 *__restrict__ ell_cs, const double *__restrict__ w_street,
+                                   Arc *__restrict__ ell)
+{
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n_slots; e += (int64_t)gridDim.x * blockDim.x) {
+        uint2 cs = ell_cs[e];
+        Arc a;
+        a.col = cs.x;
+        a.street = cs.y;
+        a.w = cs.y == 0xFFFFFFFFu ? __longlong_as_double((long long)kInfBits) : w_street[cs.y];
+        ell[e] = a;
+    }
+}
+
 __global__ void driving_speed_kernel(int64_t n, const double *length, const int32_t *max_speed, const u32 *trips,
                                      Phys ph, double *out)
 {
@@ -142,22 +156,33 @@ __global__ void driving_speed_kernel(int64_t n, const double *length, const int3
 // K2  batched multi-source SSSP, near-far (delta-stepping with one near bucket
 // and a far pile), one CTA per tree, persistent grid pulling roots from a queue.
 //
+// Layout.  Road graphs have degree <= 4 almost everywhere, so next to the CSR the
+// arcs are kept in a fixed-stride table ell[V][4] of 16-byte records (64 bytes,
+// two sectors, per node): no row_ptr lookup sits on the critical path.  Unused
+// slots hold {col = the node itself, w = +inf}, so they relax to +inf and never
+// win -- no degree branch.  Bit 31 of slot 0's col flags a node with more than 4
+// arcs; the extra arcs are read from the CSR row (rare).
+//
 // Per tree the CTA owns one distance slot dist[V] (u64 view of fp64) in the
-// pool.  A frontier entry is (node, high 32 bits of the distance it was pushed
-// with): popping it re-reads dist[node] and drops the entry if the word has
-// since improved past those bits (superseded), so a node is expanded once per
-// improvement, not once per push.  Relaxation is TILE lanes per frontier node:
-// the lanes of a tile read consecutive 16-byte arc records (one coalesced
-// request per node), then dist[head] (ld.cg), then atomicMin on the u64 view.
-// Improved heads go to the next near queue (shared memory, spilling to global)
-// when below the bucket threshold, else to the far pile (global); both pushes
-// are compacted with one warp ballot and one shared-memory atomic per warp.
+// pool.  A frontier entry is (node, exact distance it was pushed with): popping
+// needs nothing from memory before the arc fetch, and the entry is dropped when
+// dist[node] has improved since (superseded), so a node is expanded once per
+// surviving improvement.  One thread expands one node: four LDG.128 arc records
+// and the stale check in flight together, then four dist[head] loads (ld.cg),
+// then atomicMin on the u64 view.  Improved heads go to the next near queue
+// (shared memory, spilling to global) when below the bucket threshold, else to
+// the far pile (global); pushes are compacted with a warp scan and one
+// shared-memory atomic per warp and queue.
 //
 // The fixed point reached is schedule-independent and equals Dijkstra's:
 // dist[v] = min over neighbours of fl(dist[u] + w) with left-to-right rounding.
 // ---------------------------------------------------------------------------
+static constexpr int kEllWidth = 4;
+static constexpr u32 kOvfBit = 0x80000000u;
+
 struct SsspParams {
-    const u32 *row_ptr;     // V+1
+    const Arc *ell;         // V * kEllWidth
+    const u32 *row_ptr;     // V+1  (overflow arcs, fallback sweeps)
     const Arc *arcs;        // A
     u64 *dist_pool;         // n_roots slots of V words (slot i <-> roots[i])
     const int32_t *roots;   // roots of this batch
@@ -166,21 +191,77 @@ struct SsspParams {
     u32 *work_counter;      // zeroed before launch
     const double *wsum;     // sum of street weights (device scalar)
     double delta_scale;     // delta = delta_scale * wsum   (= delta_factor / S)
-    uint2 *ws_near;         // per CTA: 2 * near_gcap
-    uint2 *ws_far;          // per CTA: 2 * far_cap
+    u32 *ws_v;              // per CTA: [near0 | near1] gcap entries each, then [far0 | far1] fcap each
+    u64 *ws_d;
     u32 near_scap;          // entries per near queue in shared memory
     u32 near_gcap;          // spill entries per near queue in global memory
     u32 far_cap;            // entries per far pile
     u64 *counters;
 };
 
-template <int BLOCK, int TILE>
-__global__ void __launch_bounds__(BLOCK) sssp_nearfar_kernel(SsspParams p)
+struct Queue {
+    u32 *sv; u64 *sd;       // shared-memory part (scap entries)
+    u32 *gv; u64 *gd;       // global spill (gcap entries)
+};
+
+__device__ __forceinline__ void q_store(const Queue &q, u32 scap, u32 gcap, u32 idx, u32 v, u64 d, u32 *overflow)
 {
-    static_assert(BLOCK % 32 == 0 && 32 % TILE == 0, "tile must divide the warp");
+    if (idx < scap) { q.sv[idx] = v; q.sd[idx] = d; }
+    else if (idx - scap < gcap) { q.gv[idx - scap] = v; q.gd[idx - scap] = d; }
+    else *overflow = 1u;
+}
+
+// Warp-cooperative append of up to N candidates per lane: kind[j] 1 = near queue, 2 = far pile.
+// One scan over packed (near, far) counts, one shared-memory atomic per queue per warp.
+template <int N>
+__device__ __forceinline__ void warp_push(const u32 (&kind)[N], const u32 (&pv)[N], const u64 (&pd)[N], u32 lane,
+                                          const Queue &nq, u32 *near_cnt, u32 scap, u32 gcap, u32 *far_v, u64 *far_d,
+                                          u32 *far_cnt, u32 *far_min, u32 fcap, u32 *overflow, u64 &c_push)
+{
+    u32 packed = 0, mymin = 0xFFFFFFFFu;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        packed += (kind[j] == 1u ? 1u : 0u) + (kind[j] == 2u ? 0x10000u : 0u);
+        if (kind[j] == 2u) mymin = min(mymin, hi32(pd[j]));
+    }
+    u32 incl = packed;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane >= o) incl += t;
+    }
+    const u32 total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0u) return;                                   // warp-uniform
+    u32 base_n = 0, base_f = 0;
+    if (total >> 16) {
+        const u32 wmin = __reduce_min_sync(0xffffffffu, mymin);
+        if (lane == 31) { base_f = atomicAdd(far_cnt, total >> 16); atomicMin(far_min, wmin); }
+    }
+    if ((total & 0xFFFFu) && lane == 31) base_n = atomicAdd(near_cnt, total & 0xFFFFu);
+    base_n = __shfl_sync(0xffffffffu, base_n, 31);
+    base_f = __shfl_sync(0xffffffffu, base_f, 31);
+    const u32 excl = incl - packed;
+    u32 on = base_n + (excl & 0xFFFFu), of = base_f + (excl >> 16);
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        if (kind[j] == 1u) { q_store(nq, scap, gcap, on++, pv[j], pd[j], overflow); ++c_push; }
+        else if (kind[j] == 2u) {
+            if (of < fcap) { far_v[of] = pv[j]; far_d[of] = pd[j]; } else *overflow = 1u;
+            ++of; ++c_push;
+        }
+    }
+}
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK, (BLOCK <= 512 ? 1024 / BLOCK : 1)) sssp_nearfar_kernel(SsspParams p)
+{
+    static_assert(BLOCK % 32 == 0, "whole warps");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint2 *sq0 = reinterpret_cast<uint2 *>(smem_raw);
-    uint2 *sq1 = sq0 + p.near_scap;
+    const u32 scap = p.near_scap, gcap = p.near_gcap, fcap = p.far_cap;
+    u64 *sd0 = reinterpret_cast<u64 *>(smem_raw);
+    u64 *sd1 = sd0 + scap;
+    u32 *sv0 = reinterpret_cast<u32 *>(sd1 + scap);
+    u32 *sv1 = sv0 + scap;
     __shared__ u32 s_cnt[3];       // near queue fill counters, rotating (one barrier per round)
     __shared__ u32 s_far_cnt[2];
     __shared__ u32 s_far_min[2];   // min high word among the entries of each far pile
@@ -190,17 +271,14 @@ __global__ void __launch_bounds__(BLOCK) sssp_nearfar_kernel(SsspParams p)
 
     const u32 tid = threadIdx.x;
     const u32 lane = tid & 31u;
-    const u32 lt_mask = (1u << lane) - 1u;
-    const u32 sub = tid % TILE;
-    const u32 grp = tid / TILE;
-    constexpr u32 NG = BLOCK / TILE;
-
-    uint2 *gq0 = p.ws_near + (size_t)blockIdx.x * 2u * p.near_gcap;
-    uint2 *gq1 = gq0 + p.near_gcap;
-    uint2 *far0 = p.ws_far + (size_t)blockIdx.x * 2u * p.far_cap;
-    uint2 *far1 = far0 + p.far_cap;
-    const u32 scap = p.near_scap, gcap = p.near_gcap, fcap = p.far_cap;
     const u32 V = p.V;
+    const size_t ws_stride = (size_t)2 * gcap + (size_t)2 * fcap;
+    u32 *wv = p.ws_v + (size_t)blockIdx.x * ws_stride;
+    u64 *wd = p.ws_d + (size_t)blockIdx.x * ws_stride;
+    // queue b / far pile f by arithmetic (no dynamically indexed local arrays)
+    auto near_q = [&](u32 b_) { return Queue{sv0 + b_ * scap, sd0 + b_ * scap, wv + (size_t)b_ * gcap, wd + (size_t)b_ * gcap}; };
+    auto far_v = [&](u32 f_) { return wv + 2 * (size_t)gcap + (size_t)f_ * fcap; };
+    auto far_d = [&](u32 f_) { return wd + 2 * (size_t)gcap + (size_t)f_ * fcap; };
 
     double delta = p.delta_scale * (*p.wsum);
     if (!(delta > 0.0)) delta = 0.0;
@@ -216,10 +294,10 @@ __global__ void __launch_bounds__(BLOCK) sssp_nearfar_kernel(SsspParams p)
         u64 *dist = p.dist_pool + (size_t)ri * V;
         const u32 root = (u32)p.roots[ri];
 
-        // ---- fill the slot with +inf (16-byte stores; V*8 bytes, slot is 16-byte aligned when V is even)
+        // ---- fill the slot with +inf (16-byte stores)
         {
             const size_t base_addr = (size_t)ri * V;
-            u32 head = (u32)(base_addr & 1u);              // leading word if the slot starts on an odd word
+            const u32 head = (u32)(base_addr & 1u);        // slot starts on an odd word
             if (head && tid == 0) dist[0] = kInfBits;
             ulonglong2 *d2 = reinterpret_cast<ulonglong2 *>(dist + head);
             const u32 n2 = (V - head) >> 1;
@@ -232,7 +310,7 @@ __global__ void __launch_bounds__(BLOCK) sssp_nearfar_kernel(SsspParams p)
             s_far_cnt[0] = 0u; s_far_cnt[1] = 0u;
             s_far_min[0] = 0xFFFFFFFFu; s_far_min[1] = 0xFFFFFFFFu;
             s_overflow = 0u;
-            sq0[0] = make_uint2(root, 0u);
+            sv0[0] = root; sd0[0] = 0ull;
         }
         __syncthreads();
         if (tid == 0) dist[root] = 0ull;                   // after the fill
@@ -241,7 +319,7 @@ __global__ void __launch_bounds__(BLOCK) sssp_nearfar_kernel(SsspParams p)
         u32 c = 0;          // index of the current near counter
         u32 b = 0;          // current near buffer
         u32 f = 0;          // current far pile (push target)
-        u64 thr_bits = (u64)__double_as_longlong(delta);   // near bucket = [.., thr)
+        u32 thr_hi = hi32((u64)__double_as_longlong(delta));   // near bucket = entries with hi32(d) <= thr_hi
 
         for (;;) {
             const u32 n = s_cnt[c];
@@ -249,77 +327,73 @@ __global__ void __launch_bounds__(BLOCK) sssp_nearfar_kernel(SsspParams p)
                 // ------------------------- relaxation round -------------------------
                 const u32 cn = c == 2 ? 0 : c + 1;
                 if (tid == 0) s_cnt[cn == 2 ? 0 : cn + 1] = 0u;        // counter of the round after next
-                uint2 *qc = b ? sq1 : sq0, *gqc = b ? gq1 : gq0;
-                uint2 *qn = b ? sq0 : sq1, *gqn = b ? gq0 : gq1;
-                uint2 *farp = f ? far1 : far0;
+                const Queue qc = near_q(b);
+                const Queue qn = near_q(b ^ 1u);
+                u32 *const fv = far_v(f);
+                u64 *const fd = far_d(f);
                 const u32 n_s = n < scap + gcap ? n : scap + gcap;      // entries that were actually stored
                 ++c_round;
-                for (u32 base = 0; base < n_s; base += NG) {
-                    const u32 i = base + grp;
+                for (u32 base = 0; base < n_s; base += BLOCK) {
+                    const u32 i = base + tid;
                     bool valid = i < n_s;
-                    u32 rb = 0, deg = 0;
-                    u64 du = 0;
+                    u32 u = 0;
+                    u64 du = 0, cur = 0;
+                    Arc a[kEllWidth];
                     if (valid) {
-                        const uint2 ent = i < scap ? qc[i] : gqc[i - scap];
-                        du = ld_dist(dist + ent.x);
-                        if (hi32(du) < ent.y) {
-                            valid = false;                              // superseded by a later push
-                            if (sub == 0) ++c_stale;
-                        } else {
-                            rb = __ldg(p.row_ptr + ent.x);
-                            deg = __ldg(p.row_ptr + ent.x + 1) - rb;
-                            if (sub == 0) ++c_pop;
-                        }
+                        if (i < scap) { u = qc.sv[i]; du = qc.sd[i]; }
+                        else { u = qc.gv[i - scap]; du = qc.gd[i - scap]; }
+                        const Arc *row = p.ell + (size_t)u * kEllWidth;
+#pragma unroll
+                        for (int j = 0; j < kEllWidth; ++j) a[j] = ld_arc(row + j);
+                        cur = ld_dist(dist + u);
+                        if (cur < du) { valid = false; ++c_stale; }     // superseded by a later push
+                        else ++c_pop;
                     }
-                    for (u32 k = sub; __any_sync(0xffffffffu, valid && k < deg); k += TILE) {
-                        const bool act = valid && k < deg;
-                        bool imp = false;
-                        u32 v = 0;
-                        u64 ndb = 0;
-                        if (act) {
-                            const Arc a = ld_arc(p.arcs + rb + k);
-                            v = a.col;
-                            ndb = (u64)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)du), a.w));
-                            u64 old = ld_dist(dist + v);
-                            if (ndb < old) {
-                                old = atomicMin(dist + v, ndb);
-                                imp = ndb < old;
-                            }
-                            ++c_relax;
+                    u32 kind[kEllWidth], pv[kEllWidth];
+                    u64 pd[kEllWidth];
+#pragma unroll
+                    for (int j = 0; j < kEllWidth; ++j) { kind[j] = 0u; pv[j] = 0u; pd[j] = 0ull; }
+                    bool ovf = false;
+                    if (valid) {
+                        ovf = (a[0].col & kOvfBit) != 0u;
+                        u64 old[kEllWidth];
+#pragma unroll
+                        for (int j = 0; j < kEllWidth; ++j) {
+                            pv[j] = a[j].col & ~kOvfBit;
+                            pd[j] = (u64)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)du), a[j].w));
+                            old[j] = ld_dist(dist + pv[j]);
                         }
-                        const bool to_near = imp && ndb < thr_bits;
-                        const bool to_far = imp && !to_near;
-                        const u32 mn = __ballot_sync(0xffffffffu, to_near);
-                        if (mn) {
-                            const int leader = __ffs(mn) - 1;
-                            u32 basei = 0;
-                            if ((int)lane == leader) basei = atomicAdd(&s_cnt[cn], (u32)__popc(mn));
-                            basei = __shfl_sync(0xffffffffu, basei, leader);
-                            if (to_near) {
-                                const u32 idx = basei + (u32)__popc(mn & lt_mask);
-                                const uint2 e = make_uint2(v, hi32(ndb));
-                                if (idx < scap) qn[idx] = e;
-                                else if (idx - scap < gcap) gqn[idx - scap] = e;
-                                else s_overflow = 1u;
-                                ++c_push;
+#pragma unroll
+                        for (int j = 0; j < kEllWidth; ++j) {
+                            if (pd[j] < old[j]) {
+                                const u64 o2 = atomicMin(dist + pv[j], pd[j]);
+                                if (pd[j] < o2) kind[j] = hi32(pd[j]) <= thr_hi ? 1u : 2u;
                             }
                         }
-                        const u32 mf = __ballot_sync(0xffffffffu, to_far);
-                        if (mf) {
-                            const int leader = __ffs(mf) - 1;
-                            const u32 wmin = __reduce_min_sync(0xffffffffu, to_far ? hi32(ndb) : 0xFFFFFFFFu);
-                            u32 basei = 0;
-                            if ((int)lane == leader) {
-                                basei = atomicAdd(&s_far_cnt[f], (u32)__popc(mf));
-                                atomicMin(&s_far_min[f], wmin);
+                        c_relax += kEllWidth;
+                    }
+                    warp_push<kEllWidth>(kind, pv, pd, lane, qn, &s_cnt[cn], scap, gcap, fv, fd, &s_far_cnt[f],
+                                         &s_far_min[f], fcap, &s_overflow, c_push);
+                    // nodes with more than kEllWidth arcs: the rest of the CSR row, one arc per step
+                    if (__any_sync(0xffffffffu, ovf)) {
+                        u32 e = 0, re = 0;
+                        if (ovf) { e = __ldg(p.row_ptr + u) + kEllWidth; re = __ldg(p.row_ptr + u + 1); }
+                        while (__any_sync(0xffffffffu, e < re)) {
+                            u32 k1[1] = {0u}, v1[1] = {0u};
+                            u64 d1[1] = {0ull};
+                            if (e < re) {
+                                const Arc x = ld_arc(p.arcs + e);
+                                v1[0] = x.col;
+                                d1[0] = (u64)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)du), x.w));
+                                if (d1[0] < ld_dist(dist + x.col)) {
+                                    const u64 o2 = atomicMin(dist + x.col, d1[0]);
+                                    if (d1[0] < o2) k1[0] = hi32(d1[0]) <= thr_hi ? 1u : 2u;
+                                }
+                                ++c_relax;
+                                ++e;
                             }
-                            basei = __shfl_sync(0xffffffffu, basei, leader);
-                            if (to_far) {
-                                const u32 idx = basei + (u32)__popc(mf & lt_mask);
-                                if (idx < fcap) farp[idx] = make_uint2(v, hi32(ndb));
-                                else s_overflow = 1u;
-                                ++c_push;
-                            }
+                            warp_push<1>(k1, v1, d1, lane, qn, &s_cnt[cn], scap, gcap, fv, fd, &s_far_cnt[f],
+                                         &s_far_min[f], fcap, &s_overflow, c_push);
                         }
                     }
                 }
@@ -332,48 +406,31 @@ __global__ void __launch_bounds__(BLOCK) sssp_nearfar_kernel(SsspParams p)
             const u32 nf_raw = s_far_cnt[f];
             if (nf_raw == 0u) break;                                    // tree complete
             const u32 nf = nf_raw < fcap ? nf_raw : fcap;
+            const u32 far_min_hi = s_far_min[f];
+            // every thread must have seen s_cnt[c] == 0 before the split starts refilling that queue
+            __syncthreads();
             ++c_adv;
             // new threshold: smallest (lower bound of a) distance in the pile + delta
-            const double lo = __longlong_as_double((long long)((u64)s_far_min[f] << 32));
-            const double thr = __dadd_rn(lo, delta);
-            thr_bits = (u64)__double_as_longlong(thr);
-            const u32 thr_hi = hi32(thr_bits);
-            uint2 *src = f ? far1 : far0;
-            uint2 *dst = f ? far0 : far1;
-            uint2 *qc = b ? sq1 : sq0, *gqc = b ? gq1 : gq0;            // the round after this reads (b, c)
+            const double lo = __longlong_as_double((long long)((u64)far_min_hi << 32));
+            thr_hi = hi32((u64)__double_as_longlong(__dadd_rn(lo, delta)));
             const u32 fo = f ^ 1u;
+            const u32 *srcv = far_v(f);
+            const u64 *srcd = far_d(f);
+            const Queue qb = near_q(b);
+            u32 *const dv = far_v(fo);
+            u64 *const dd = far_d(fo);
             for (u32 base = 0; base < nf; base += BLOCK) {
                 const u32 i = base + tid;
-                const bool have = i < nf;
-                uint2 e = make_uint2(0u, 0u);
-                if (have) e = src[i];
-                const bool to_near = have && e.y <= thr_hi;
-                const bool keep = have && !to_near;
-                const u32 mn = __ballot_sync(0xffffffffu, to_near);
-                if (mn) {
-                    const int leader = __ffs(mn) - 1;
-                    u32 basei = 0;
-                    if ((int)lane == leader) basei = atomicAdd(&s_cnt[c], (u32)__popc(mn));
-                    basei = __shfl_sync(0xffffffffu, basei, leader);
-                    if (to_near) {
-                        const u32 idx = basei + (u32)__popc(mn & lt_mask);
-                        if (idx < scap) qc[idx] = e;
-                        else if (idx - scap < gcap) gqc[idx - scap] = e;
-                        else s_overflow = 1u;
-                    }
+                u32 k1[1] = {0u}, v1[1] = {0u};
+                u64 d1[1] = {0ull};
+                if (i < nf) {
+                    v1[0] = srcv[i];
+                    d1[0] = srcd[i];
+                    k1[0] = hi32(d1[0]) <= thr_hi ? 1u : 2u;
                 }
-                const u32 mk = __ballot_sync(0xffffffffu, keep);
-                if (mk) {
-                    const int leader = __ffs(mk) - 1;
-                    const u32 wmin = __reduce_min_sync(0xffffffffu, keep ? e.y : 0xFFFFFFFFu);
-                    u32 basei = 0;
-                    if ((int)lane == leader) {
-                        basei = atomicAdd(&s_far_cnt[fo], (u32)__popc(mk));
-                        atomicMin(&s_far_min[fo], wmin);
-                    }
-                    basei = __shfl_sync(0xffffffffu, basei, leader);
-                    if (keep) dst[basei + (u32)__popc(mk & lt_mask)] = e;   // never exceeds nf <= fcap
-                }
+                // the round after this reads (b, c); kept entries go to the other pile (never more than nf)
+                warp_push<1>(k1, v1, d1, lane, qb, &s_cnt[c], scap, gcap, dv, dd, &s_far_cnt[fo],
+                             &s_far_min[fo], fcap, &s_overflow, c_push);
             }
             __syncthreads();
             if (tid == 0) { s_far_cnt[f] = 0u; s_far_min[f] = 0xFFFFFFFFu; }
@@ -396,10 +453,10 @@ __global__ void __launch_bounds__(BLOCK) sssp_nearfar_kernel(SsspParams p)
                     if (du >= kInfBits) continue;
                     const u32 rb = __ldg(p.row_ptr + u), re = __ldg(p.row_ptr + u + 1);
                     for (u32 e = rb; e < re; ++e) {
-                        const Arc a = ld_arc(p.arcs + e);
-                        const u64 ndb = (u64)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)du), a.w));
-                        if (ndb < ld_dist(dist + a.col)) {
-                            atomicMin(dist + a.col, ndb);
+                        const Arc x = ld_arc(p.arcs + e);
+                        const u64 ndb = (u64)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)du), x.w));
+                        if (ndb < ld_dist(dist + x.col)) {
+                            atomicMin(dist + x.col, ndb);
                             any = true;
                         }
                     }
@@ -417,6 +474,309 @@ __global__ void __launch_bounds__(BLOCK) sssp_nearfar_kernel(SsspParams p)
 #pragma unroll
     for (int j = 0; j < 7; ++j) {
         u64 v = vals[j];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0 && v) atomicAdd(p.counters + ids[j], v);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K2, barrier-free variant.  Same data layout, same entries, same fixed point as
+// sssp_nearfar_kernel, but inside a bucket the warps of the CTA do not meet at a
+// barrier per round: the near queue is one ring in shared memory, every warp
+// claims up to 32 ready entries (CAS on the head), expands them and appends the
+// improved heads to the same ring (reserve on the tail, per-slot ready flag), so
+// a warp never waits for the slowest memory access of another warp.  The bucket
+// is finished when every reserved entry has been processed (done == tail); only
+// then the CTA synchronises, splits the far pile and refills the ring.  A full
+// ring simply diverts pushes to the far pile (they come back at a later split).
+// ---------------------------------------------------------------------------
+static constexpr u32 kSlotEmpty = 0xFFFFFFFFu;
+
+__device__ __forceinline__ u32 ld_vol(const u32 *p) { return *reinterpret_cast<const volatile u32 *>(p); }
+
+struct Ring {
+    u32 *rv; u64 *rd;       // rcap slots (power of two); rv == kSlotEmpty: not written yet
+    u32 mask;               // rcap - 1
+    u32 limit;              // pushes go to the far pile once tail - done would exceed this
+    u32 *head, *tail, *done;
+};
+
+// Warp-cooperative append: kind[j] 1 = ring, 2 = far pile.  Ring candidates fall back to the
+// far pile when the ring is (conservatively) full.
+template <int N>
+__device__ __forceinline__ void warp_push_async(u32 (&kind)[N], const u32 (&pv)[N], const u64 (&pd)[N], u32 lane,
+                                                const Ring &R, u32 *far_v, u64 *far_d, u32 *far_cnt, u32 *far_min,
+                                                u32 fcap, u32 *overflow, u64 &c_push)
+{
+    u32 packed = 0;
+#pragma unroll
+    for (int j = 0; j < N; ++j) packed += (kind[j] == 1u ? 1u : 0u) + (kind[j] == 2u ? 0x10000u : 0u);
+    u32 incl = packed;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane >= o) incl += t;
+    }
+    u32 total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0u) return;                                   // warp-uniform
+    u32 base_n = 0, ring_ok = 1;
+    if (total & 0xFFFFu) {
+        if (lane == 31) {
+            const u32 t = ld_vol(R.tail), d = ld_vol(R.done);
+            if (t - d + (total & 0xFFFFu) > R.limit) ring_ok = 0u;
+            else base_n = atomicAdd(R.tail, total & 0xFFFFu);
+        }
+        ring_ok = __shfl_sync(0xffffffffu, ring_ok, 31);
+        base_n = __shfl_sync(0xffffffffu, base_n, 31);
+    }
+    u32 excl = incl - packed;
+    if (!ring_ok) {
+        // ring full: every candidate of this warp goes to the far pile
+        excl = (excl & 0xFFFFu) + (excl >> 16);
+        total = ((total & 0xFFFFu) + (total >> 16)) << 16;
+#pragma unroll
+        for (int j = 0; j < N; ++j) if (kind[j] == 1u) kind[j] = 2u;
+        excl <<= 16;
+    }
+    u32 base_f = 0;
+    if (total >> 16) {
+        u32 mymin = 0xFFFFFFFFu;
+#pragma unroll
+        for (int j = 0; j < N; ++j) if (kind[j] == 2u) mymin = min(mymin, hi32(pd[j]));
+        const u32 wmin = __reduce_min_sync(0xffffffffu, mymin);
+        if (lane == 31) { base_f = atomicAdd(far_cnt, total >> 16); atomicMin(far_min, wmin); }
+        base_f = __shfl_sync(0xffffffffu, base_f, 31);
+    }
+    u32 on = base_n + (excl & 0xFFFFu), of = base_f + (excl >> 16);
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        if (kind[j] == 1u) {
+            const u32 slot = on & R.mask;
+            while (ld_vol(R.rv + slot) != kSlotEmpty) { }       // previous lap's entry not read yet (never in practice)
+            R.rd[slot] = pd[j];
+            __threadfence_block();                              // distance before the ready flag
+            *reinterpret_cast<volatile u32 *>(R.rv + slot) = pv[j];
+            ++on; ++c_push;
+        } else if (kind[j] == 2u) {
+            if (of < fcap) { far_v[of] = pv[j]; far_d[of] = pd[j]; } else *overflow = 1u;
+            ++of; ++c_push;
+        }
+    }
+}
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK, (BLOCK <= 512 ? 1024 / BLOCK : 1)) sssp_async_kernel(SsspParams p)
+{
+    static_assert(BLOCK % 32 == 0, "whole warps");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const u32 rcap = p.near_scap;                  // power of two
+    const u32 fcap = p.far_cap;
+    u64 *rd = reinterpret_cast<u64 *>(smem_raw);
+    u32 *rv = reinterpret_cast<u32 *>(rd + rcap);
+    __shared__ u32 s_head, s_tail, s_done;
+    __shared__ u32 s_far_cnt[2];
+    __shared__ u32 s_far_min[2];
+    __shared__ int s_root_idx;
+    __shared__ u32 s_overflow;
+    __shared__ u32 s_changed;
+
+    const u32 tid = threadIdx.x;
+    const u32 lane = tid & 31u;
+    const u32 V = p.V;
+    const size_t ws_stride = (size_t)2 * p.near_gcap + (size_t)2 * fcap;
+    u32 *wv = p.ws_v + (size_t)blockIdx.x * ws_stride + 2 * (size_t)p.near_gcap;   // the two far piles
+    u64 *wd = p.ws_d + (size_t)blockIdx.x * ws_stride + 2 * (size_t)p.near_gcap;
+    Ring R;
+    R.rv = rv; R.rd = rd; R.mask = rcap - 1u;
+    R.limit = rcap - (BLOCK / 32) * 32u * kEllWidth;          // room for one concurrent push of every warp
+    R.head = &s_head; R.tail = &s_tail; R.done = &s_done;
+
+    double delta = p.delta_scale * (*p.wsum);
+    if (!(delta > 0.0)) delta = 0.0;
+    for (u32 i = tid; i < rcap; i += BLOCK) rv[i] = kSlotEmpty;
+
+    u64 c_relax = 0, c_pop = 0, c_stale = 0, c_push = 0, c_adv = 0, c_round = 0, c_sweep = 0;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_root_idx = (int)atomicAdd(p.work_counter, 1u);
+        __syncthreads();
+        const int ri = s_root_idx;
+        if (ri >= p.n_roots) break;
+        u64 *dist = p.dist_pool + (size_t)ri * V;
+        const u32 root = (u32)p.roots[ri];
+        {
+            const size_t base_addr = (size_t)ri * V;
+            const u32 head = (u32)(base_addr & 1u);
+            if (head && tid == 0) dist[0] = kInfBits;
+            ulonglong2 *d2 = reinterpret_cast<ulonglong2 *>(dist + head);
+            const u32 n2 = (V - head) >> 1;
+            const ulonglong2 inf2 = make_ulonglong2(kInfBits, kInfBits);
+            for (u32 i = tid; i < n2; i += BLOCK) d2[i] = inf2;
+            if (((V - head) & 1u) && tid == 0) dist[V - 1] = kInfBits;
+        }
+        if (tid == 0) {
+            s_head = 0u; s_tail = 1u; s_done = 0u;
+            s_far_cnt[0] = 0u; s_far_cnt[1] = 0u;
+            s_far_min[0] = 0xFFFFFFFFu; s_far_min[1] = 0xFFFFFFFFu;
+            s_overflow = 0u;
+            rd[0] = 0ull; rv[0] = root;
+        }
+        __syncthreads();
+        if (tid == 0) dist[root] = 0ull;
+        __syncthreads();
+
+        u32 f = 0;
+        u32 thr_hi = hi32((u64)__double_as_longlong(delta));
+
+        for (;;) {
+            // ------------------------- bucket phase: warps run free -------------------------
+            u32 *const fv = wv + (size_t)f * fcap;
+            u64 *const fd = wd + (size_t)f * fcap;
+            for (;;) {
+                u32 start = 0, n = 0;
+                if (lane == 0) {
+                    for (;;) {
+                        const u32 h = ld_vol(&s_head), t = ld_vol(&s_tail);
+                        if (t != h) {
+                            const u32 k = min(32u, t - h);
+                            if (atomicCAS(&s_head, h, h + k) == h) { start = h; n = k; break; }
+                            continue;
+                        }
+                        if (ld_vol(&s_done) == t && ld_vol(&s_tail) == t) { n = 0xFFFFFFFFu; break; }   // bucket drained
+                        __nanosleep(40);
+                    }
+                }
+                start = __shfl_sync(0xffffffffu, start, 0);
+                n = __shfl_sync(0xffffffffu, n, 0);
+                if (n == 0xFFFFFFFFu) break;
+                ++c_round;
+                bool valid = lane < n;
+                u32 u = 0;
+                u64 du = 0, cur = 0;
+                Arc a[kEllWidth];
+                if (valid) {
+                    const u32 slot = (start + lane) & R.mask;
+                    while ((u = ld_vol(rv + slot)) == kSlotEmpty) { }           // reserved, being written
+                    __threadfence_block();
+                    du = *reinterpret_cast<volatile u64 *>(rd + slot);
+                    *reinterpret_cast<volatile u32 *>(rv + slot) = kSlotEmpty;  // recycle before `done` moves
+                    const Arc *row = p.ell + (size_t)u * kEllWidth;
+#pragma unroll
+                    for (int j = 0; j < kEllWidth; ++j) a[j] = ld_arc(row + j);
+                    cur = ld_dist(dist + u);
+                    if (cur < du) { valid = false; ++c_stale; }
+                    else ++c_pop;
+                }
+                u32 kind[kEllWidth], pv[kEllWidth];
+                u64 pd[kEllWidth];
+#pragma unroll
+                for (int j = 0; j < kEllWidth; ++j) { kind[j] = 0u; pv[j] = 0u; pd[j] = 0ull; }
+                bool ovf = false;
+                if (valid) {
+                    ovf = (a[0].col & kOvfBit) != 0u;
+                    u64 old[kEllWidth];
+#pragma unroll
+                    for (int j = 0; j < kEllWidth; ++j) {
+                        pv[j] = a[j].col & ~kOvfBit;
+                        pd[j] = (u64)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)du), a[j].w));
+                        old[j] = ld_dist(dist + pv[j]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < kEllWidth; ++j) {
+                        if (pd[j] < old[j]) {
+                            const u64 o2 = atomicMin(dist + pv[j], pd[j]);
+                            if (pd[j] < o2) kind[j] = hi32(pd[j]) <= thr_hi ? 1u : 2u;
+                        }
+                    }
+                    c_relax += kEllWidth;
+                }
+                warp_push_async<kEllWidth>(kind, pv, pd, lane, R, fv, fd, &s_far_cnt[f], &s_far_min[f], fcap, &s_overflow, c_push);
+                if (__any_sync(0xffffffffu, ovf)) {
+                    u32 e = 0, re = 0;
+                    if (ovf) { e = __ldg(p.row_ptr + u) + kEllWidth; re = __ldg(p.row_ptr + u + 1); }
+                    while (__any_sync(0xffffffffu, e < re)) {
+                        u32 k1[1] = {0u}, v1[1] = {0u};
+                        u64 d1[1] = {0ull};
+                        if (e < re) {
+                            const Arc x = ld_arc(p.arcs + e);
+                            v1[0] = x.col;
+                            d1[0] = (u64)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)du), x.w));
+                            if (d1[0] < ld_dist(dist + x.col)) {
+                                const u64 o2 = atomicMin(dist + x.col, d1[0]);
+                                if (d1[0] < o2) k1[0] = hi32(d1[0]) <= thr_hi ? 1u : 2u;
+                            }
+                            ++c_relax;
+                            ++e;
+                        }
+                        warp_push_async<1>(k1, v1, d1, lane, R, fv, fd, &s_far_cnt[f], &s_far_min[f], fcap, &s_overflow, c_push);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) { __threadfence_block(); atomicAdd(&s_done, n); }
+            }
+            __syncthreads();                                            // bucket drained, ring empty
+            // ------------------------- advance the bucket -------------------------
+            const u32 nf_raw = s_far_cnt[f];
+            if (nf_raw == 0u) break;                                    // tree complete
+            const u32 nf = nf_raw < fcap ? nf_raw : fcap;
+            const u32 far_min_hi = s_far_min[f];
+            ++c_adv;
+            const double lo = __longlong_as_double((long long)((u64)far_min_hi << 32));
+            thr_hi = hi32((u64)__double_as_longlong(__dadd_rn(lo, delta)));
+            const u32 fo = f ^ 1u;
+            const u32 *srcv = wv + (size_t)f * fcap;
+            const u64 *srcd = wd + (size_t)f * fcap;
+            for (u32 base = 0; base < nf; base += BLOCK) {
+                const u32 i = base + tid;
+                u32 k1[1] = {0u}, v1[1] = {0u};
+                u64 d1[1] = {0ull};
+                if (i < nf) {
+                    v1[0] = srcv[i];
+                    d1[0] = srcd[i];
+                    k1[0] = hi32(d1[0]) <= thr_hi ? 1u : 2u;
+                }
+                warp_push_async<1>(k1, v1, d1, lane, R, wv + (size_t)fo * fcap, wd + (size_t)fo * fcap, &s_far_cnt[fo],
+                                   &s_far_min[fo], fcap, &s_overflow, c_push);
+            }
+            __syncthreads();
+            if (tid == 0) { s_far_cnt[f] = 0u; s_far_min[f] = 0xFFFFFFFFu; }
+            f = fo;
+            __syncthreads();
+        }
+
+        if (s_overflow) {
+            for (;;) {
+                __syncthreads();
+                if (tid == 0) s_changed = 0u;
+                __syncthreads();
+                ++c_sweep;
+                bool any = false;
+                for (u32 u = tid; u < V; u += BLOCK) {
+                    const u64 du = ld_dist(dist + u);
+                    if (du >= kInfBits) continue;
+                    const u32 rb = __ldg(p.row_ptr + u), re = __ldg(p.row_ptr + u + 1);
+                    for (u32 e = rb; e < re; ++e) {
+                        const Arc x = ld_arc(p.arcs + e);
+                        const u64 ndb = (u64)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)du), x.w));
+                        if (ndb < ld_dist(dist + x.col)) {
+                            atomicMin(dist + x.col, ndb);
+                            any = true;
+                        }
+                    }
+                }
+                if (any) s_changed = 1u;
+                __syncthreads();
+                if (!s_changed) break;
+            }
+        }
+    }
+
+    u64 vals[7] = {c_relax, c_pop, c_stale, c_push, tid == 0 ? c_adv : 0, c_round, tid == 0 ? c_sweep : 0};
+    const int ids[7] = {C_ARCS_RELAXED, C_NODES_POPPED, C_STALE_POPS, C_PUSHES, C_ADVANCES, C_ROUNDS, C_FALLBACK_SWEEPS};
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+        u64 v = j == 5 ? (lane == 0 ? vals[j] : 0) : vals[j];
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         if (lane == 0 && v) atomicAdd(p.counters + ids[j], v);
     }

@@ -34,7 +34,6 @@ device_settings = {
     # SSSP kernel tunables (None = library default), see include/s4mpi.h s4_ctx_set_option
     "delta_factor": None,
     "block_threads": None,
-    "tile": None,
     "ctas_per_sm": None,
     "pool_bytes": None,
     "batch_roots": None,

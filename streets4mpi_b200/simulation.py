@@ -35,7 +35,7 @@ class Simulation(object):
         self.step_counter = 0
 
         self._device = device or engine.default_device()
-        for key in ("delta_factor", "block_threads", "tile", "ctas_per_sm", "pool_bytes", "batch_roots", "root_mode"):
+        for key in ("delta_factor", "block_threads", "ctas_per_sm", "pool_bytes", "batch_roots", "root_mode"):
             if device_settings.get(key) is not None:
                 self._device.set_option(key, device_settings[key])
         flat = street_network.flat()

@@ -17,11 +17,28 @@ ap.add_argument("--planar", type=int, default=0)
 ap.add_argument("--roots", type=int, default=1184)
 ap.add_argument("--configs", type=str, default="")
 ap.add_argument("--days", type=int, default=2)
+ap.add_argument("--morton", type=int, default=0)
 args = ap.parse_args()
 
 dev = engine.default_device()
 arr = synth.planar_arrays(args.planar, seed=1) if args.planar else synth.grid_arrays(args.rows, args.cols, seed=1)
 V = len(arr["node_ids"])
+if args.morton and not args.planar:
+    # experiment: renumber the grid nodes along a Z-order curve (2x2 nodes per 32-byte sector of dist[])
+    def spread(x):
+        x = x.astype(np.uint64)
+        x = (x | (x << 16)) & 0x0000FFFF0000FFFF
+        x = (x | (x << 8)) & 0x00FF00FF00FF00FF
+        x = (x | (x << 4)) & 0x0F0F0F0F0F0F0F0F
+        x = (x | (x << 2)) & 0x3333333333333333
+        x = (x | (x << 1)) & 0x5555555555555555
+        return x
+    ids = arr["node_ids"]
+    r, c = ids // args.cols, ids % args.cols
+    key = spread(c) | (spread(r) << 1)
+    rank = np.empty(V, dtype=np.int64)
+    rank[np.argsort(key, kind="stable")] = np.arange(V)
+    arr["u"], arr["v"] = rank[arr["u"]], rank[arr["v"]]
 cats = synth.node_categories(arr["node_ids"], seed=1)
 rng = np.random.default_rng(0)
 origins = rng.choice(arr["node_ids"], size=args.roots, replace=False)
