@@ -1,0 +1,431 @@
+#!/usr/bin/env python3
+"""Benchmark of the per-day traffic-assignment hot path (BASELINE.json metric: routed trips/s
+and GTEPS; sim-day time against the CPU reference path).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, sm_100a)
+    python bench.py --impl reference --steps K --warmup W     # the reference's CPU algorithm (oracle port)
+
+A step is one simulated day: K1 weights -> K2 one shortest-path tree per root -> K3 walk of every
+trip -> exchange (NCCL all-reduce of the uint32 load + cumulative merge).  Workload (config.workload):
+BASELINE.json configs[2], the synthetic 1024x1024 grid (V=1,048,576 S=2,095,104 A=4,190,208), 1M
+trips/day in total, goals = seeded 2 % node sample, one virtual rank (own trip stream and jam
+tolerance, streets4mpi.py:50-51,69,78) per GPU.
+
+One JSON line on rank 0.  `value` = trips routed per second by the whole job with everything resident
+in HBM (CUDA events, max over ranks); `e2e` = the same through the reference-facing Python API with
+host arrays (array('I') traffic_load assigned / read every day, host<->device copies inside the timed
+region); `roofline` = the SSSP kernel against the measured HBM copy bandwidth; `cpu_baseline` = the
+oracle's C twin on this box's host cores on a bounded sample of the same day.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+RANDOM_SEED = 3756917          # settings.py:29
+WORKLOADS = {
+    # name: (rows, cols, trips per day in total)
+    "cfg3_grid1024": (1024, 1024, 1_000_000),
+    "grid256": (256, 256, 100_000),           # quick functional run
+}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# workload (identical for both arms)
+# ----------------------------------------------------------------------------------------------
+def make_workload(name, world):
+    from streets4mpi_b200 import synth
+    rows, cols, trips_total = WORKLOADS[name]
+    arrays = synth.grid_arrays(rows, cols, seed=1)
+    cats = synth.node_categories(arrays["node_ids"], seed=1, goal_fraction=0.02)
+    per_rank = trips_total // world                       # streets4mpi.py:69
+    return arrays, cats, per_rank
+
+
+def rank_trips(arrays, cats, per_rank, rank):
+    """Trip arrays and jam tolerance of one virtual rank (streets4mpi.py:50-51,75,78)."""
+    from streets4mpi_b200 import synth
+    seed = RANDOM_SEED + 37 * rank
+    o, g = synth.trip_arrays(per_rank, arrays["node_ids"], cats["goals"], seed=seed)
+    jam = float(np.random.default_rng(seed ^ 0x5DEECE66D).random())
+    return o, g, jam
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        busy = sorted(sm)[len(sm) // 2:]                      # upper half = samples under load
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arms (oracle: test infrastructure / reported baseline only)
+# ----------------------------------------------------------------------------------------------
+def cpu_sample(arrays, o, g, jam, seconds_target, threads):
+    """Oracle C twin (oracle/c/s4_oracle.c) on a bounded sample of the day's origins, the reference's
+    grouping (one tree per distinct origin, simulation.py:71).  Returns (trips/s, description)."""
+    from oracle import ctwin
+    ctwin.build()
+    V = len(arrays["node_ids"])
+    csr = ctwin.Csr(V, arrays["u"], arrays["v"])
+    w = ctwin.weights(arrays["length"], arrays["max_speed"], np.zeros(len(arrays["u"]), dtype=np.uint32), jam)
+    roots, off, tg = ctwin.group_trips(o.astype(np.int32), g.astype(np.int32))
+    # calibrate on `threads` trees, then size the sample for ~seconds_target
+    def run(n_roots):
+        sel = np.arange(n_roots)
+        oo = np.repeat(roots[sel], np.diff(off)[sel])
+        gg = np.concatenate([tg[off[i]:off[i + 1]] for i in sel]) if n_roots else np.zeros(0, np.int32)
+        t0 = time.perf_counter()
+        _load, cnt = ctwin.day(csr, w, oo, gg, nthreads=threads)
+        return time.perf_counter() - t0, len(oo), cnt
+    t_cal, _, _ = run(min(len(roots), threads))
+    n = int(max(threads, min(len(roots), threads * seconds_target / max(t_cal, 1e-3))))
+    t, trips, cnt = run(n)
+    desc = ("%d of %d distinct origins of the day (%d trips), binary-heap Dijkstra + canonical walk, %d threads, %.1f s"
+            % (n, len(roots), trips, threads, t))
+    return trips / t, desc, dict(trees=n, trips=trips, seconds=t, trees_per_s=n / t)
+
+
+_REF_GRAPH = None      # (row_ptr, col, arc_w) lists, inherited by the forked workers
+
+
+def _py_tree_worker(jobs):
+    """Pure-Python heapq Dijkstra + walk for a few origins: the reference algorithm at the reference's
+    language level (simulation.py:71-88 over python-graph's strict-'<' Dijkstra)."""
+    import heapq
+    row_ptr, col, arc_w = _REF_GRAPH
+    hops = 0
+    t0 = time.perf_counter()
+    for origin, goals in jobs:
+        dist = {origin: 0.0}
+        prev = {origin: None}
+        done = set()
+        heap = [(0.0, origin)]
+        while heap:
+            du, u = heapq.heappop(heap)
+            if u in done:
+                continue
+            done.add(u)
+            for e in range(row_ptr[u], row_ptr[u + 1]):
+                v = col[e]
+                if v in done:
+                    continue
+                alt = du + arc_w[e]
+                if v not in dist or alt < dist[v]:
+                    dist[v] = alt
+                    prev[v] = u
+                    heapq.heappush(heap, (alt, v))
+        for goal in goals:
+            if goal in prev:
+                cur = goal
+                while cur != origin:
+                    cur = prev[cur]
+                    hops += 1
+    return time.perf_counter() - t0, hops
+
+
+def reference_arm(args):
+    """--impl reference: the reference's CPU path.  The reference itself (Python 2 + python-graph +
+    mpi4py + imposm) cannot run in this image (DESIGN.md 'Oracle'), so this times the oracle port: a
+    pure-Python Dijkstra per distinct origin, one process per host core standing in for
+    `mpiexec -n <cores>`, on a bounded sample of the same day."""
+    import multiprocessing as mp
+    from oracle import ctwin
+    cores = os.cpu_count() or 1
+    arrays, cats, per_rank = make_workload(args.workload, 1)
+    o, g, jam = rank_trips(arrays, cats, per_rank, 0)
+    V = len(arrays["node_ids"])
+    csr = ctwin.Csr(V, arrays["u"], arrays["v"])
+    w = ctwin.weights(arrays["length"], arrays["max_speed"], np.zeros(len(arrays["u"]), dtype=np.uint32), jam)
+    roots, off, tg = ctwin.group_trips(o.astype(np.int32), g.astype(np.int32))
+    global _REF_GRAPH
+    _REF_GRAPH = (csr.row_ptr.tolist(), csr.col.tolist(), w[csr.arc_street].tolist())
+    per_step = args.ref_trees_per_core * cores
+    steps = args.warmup + args.steps
+    times, trips_done = [], []
+    with mp.get_context("fork").Pool(cores) as pool:
+        for s in range(steps):
+            sel = [(s * per_step + i) % len(roots) for i in range(per_step)]
+            jobs = [(int(roots[i]), tg[off[i]:off[i + 1]].tolist()) for i in sel]
+            chunks = [jobs[c::cores] for c in range(cores)]
+            t0 = time.perf_counter()
+            pool.map(_py_tree_worker, chunks)
+            dt = time.perf_counter() - t0
+            if s >= args.warmup:
+                times.append(dt)
+                trips_done.append(int(sum(off[i + 1] - off[i] for i in sel)))
+    total_t = sum(times)
+    value = sum(trips_done) / total_t
+    sample = ("%d distinct origins per step (%d per core) of %d; full day extrapolates linearly in the number of "
+              "distinct origins" % (per_step, args.ref_trees_per_core, len(roots)))
+    line = {
+        "impl": "reference", "metric": "routed_trips_per_sec", "value": value, "unit": "trips/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / max(1, args.steps),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload + ": " + workload_text(args.workload), "root_mode": "origin (reference grouping)",
+                   "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "trips/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "trips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_text(name):
+    rows, cols, trips = WORKLOADS[name]
+    return ("synthetic %dx%d grid street network (V=%d, S=%d, A=%d), %d trips/day, goals = 2%% node sample, "
+            "BASELINE.json configs[2]" % (rows, cols, rows * cols, 2 * rows * cols - rows - cols,
+                                          2 * (2 * rows * cols - rows - cols), trips))
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def gpu_arm(args):
+    import torch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    from streets4mpi_b200 import Simulation, TripTable, distributed, engine, synth
+    from streets4mpi_b200.settings import device_settings, settings
+
+    stream = torch.cuda.Stream(device=local)
+    dev = engine.Device(local, stream=stream.cuda_stream)
+    engine.set_default_device(dev)
+    device_settings["root_mode"] = {"origin": 0, "goal": 1, "auto": 2}[args.root_mode]
+    for kv in filter(None, args.options.split(",")):
+        k, v = kv.split("=")
+        device_settings[k] = float(v)
+        dev.set_option(k, float(v))
+    settings["logging"] = None
+
+    arrays, cats, per_rank = make_workload(args.workload, world)
+    o, g, jam = rank_trips(arrays, cats, per_rank, rank)
+    net = synth.network_from(arrays)
+    t0 = time.perf_counter()
+    sim = Simulation(net, TripTable(o, g), jam, lambda *a: None, device=dev)
+    dev.sync()
+    setup_s = time.perf_counter() - t0
+    S = sim._sim.S
+    mode = {0: "origin", 1: "goal", 2: "auto"}[sim._sim.root_mode]
+    log("[rank %d] setup %.1f s, %d trips, %d trees/day (%s-rooted), jam %.3f" % (rank, setup_s, per_rank, sim._sim.n_roots, mode, jam))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(local)
+
+    def day_resident():
+        with torch.cuda.stream(stream):
+            sim.step()
+            sim.exchange()
+
+    # ---- resident-in-HBM timing: W warm-up days, then exactly K days between two events
+    for _ in range(args.warmup):
+        day_resident()
+    barrier()
+    sim._sim.reset_counters()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(args.steps):
+            sim.step()
+            sim.exchange()
+        e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    c = sim.counters()
+    t_ms = torch.tensor([ms], dtype=torch.float64, device="cuda:%d" % local)
+    agg = torch.tensor([c["sssp_instances"], c["arcs_algorithmic"], c["nodes_algorithmic"], c["trips_routed"],
+                        c["kernel_launches"], c["hops"], c["arcs_relaxed"]], dtype=torch.float64, device="cuda:%d" % local)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+    ms_max = float(t_ms.item())
+    trees, arcs_alg, nodes_alg, trips, launches, hops, arcs_rel = [float(x) for x in agg.tolist()]
+
+    # ---- end to end through the reference-facing API: host arrays every day (streets4mpi.py:93-100)
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    from streets4mpi_b200 import merge_arrays
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        with torch.cuda.stream(stream):
+            sim.step()                                      # uploads what the driver assigned yesterday (H2D 8*S)
+            local_load = sim.traffic_load                   # D2H 4*S -> array('I')
+            total = distributed.allreduce_array_I(local_load) if world > 1 else local_load   # :97-98
+            sim.traffic_load = total                        # :99
+            sim.cumulative_traffic_load = merge_arrays((total, sim.cumulative_traffic_load))   # :100
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t_e2e = torch.tensor([e2e_s], dtype=torch.float64, device="cuda:%d" % local)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_s = float(t_e2e.item())
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        alg_bytes = 20.0 * c["arcs_algorithmic"] + 20.0 * c["nodes_algorithmic"]          # rank 0's launches
+        n_launch = max(1, c["sssp_launches"])
+        ms_launch = c["ms_sssp"] / n_launch
+        achieved = alg_bytes / n_launch / (ms_launch * 1e-3) / 1e9 if ms_launch > 0 else 0.0
+        traffic = None
+        prof = os.path.join(ROOT, "profiles", "sssp_dram_bytes_per_tree.json")
+        if os.path.exists(prof):
+            try:
+                traffic = json.load(open(prof))["dram_bytes_per_tree"] * c["sssp_instances"] / n_launch
+            except Exception:
+                traffic = None
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            v, desc, _ = cpu_sample(arrays, net.flat().dense(o), net.flat().dense(g), jam, args.cpu_seconds, threads)
+            cpu = {"value": v, "unit": "trips/s", "cores": threads, "kind": "port", "sample": desc}
+        total_trips = per_rank * world * args.steps
+        line = {
+            "metric": "routed_trips_per_sec", "value": total_trips / (ms_max * 1e-3), "unit": "trips/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload + ": " + workload_text(args.workload),
+                       "root_mode": "%s (trees per day and GPU: %d)" % (mode, sim._sim.n_roots),
+                       "virtual_ranks": world, "l2": "inputs larger than L2 (distance pool %.1f GB per GPU)"
+                       % (min(sim._sim.n_roots, 3000) * 8.0 * len(arrays["node_ids"]) / 1e9),
+                       "options": args.options or "defaults"},
+            "gteps": arcs_alg / (ms_max * 1e-3) / 1e9,
+            "sssp_trees_per_sec": trees / (ms_max * 1e-3),
+            "relaxations_per_algorithmic_arc": arcs_rel / max(1.0, arcs_alg),
+            "hops_per_trip": hops / max(1.0, trips),
+            "kernel_ms_per_step": {"weights": c["ms_weights"] / args.steps, "sssp": c["ms_sssp"] / args.steps,
+                                   "walk": c["ms_walk"] / args.steps},
+            "roofline": {"bound": "hbm", "kernel": "sssp", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes / n_launch, "ms_per_launch": ms_launch,
+                         "launches": n_launch},
+            "cpu_baseline": cpu,
+            "e2e": {"value": per_rank * world * e2e_steps / e2e_s, "unit": "trips/s", "steps": e2e_steps,
+                    "h2d_bytes_per_step": 8 * S, "d2h_bytes_per_step": 4 * S,
+                    "api": "reference driver protocol (streets4mpi.py:93-100): Simulation.step(), array('I') "
+                           "traffic_load read + assign, merge_arrays into cumulative_traffic_load; wall clock"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "setup_seconds": setup_s,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="cfg3_grid1024")
+    ap.add_argument("--root-mode", choices=["origin", "goal", "auto"], default="auto")
+    ap.add_argument("--options", default="", help="library options, key=value,...")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-trees-per-core", type=int, default=1)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -101,10 +101,15 @@ def exchange(simulations, group=None):
         import torch.distributed as dist
         if dist.is_initialized():
             dev = sims[0]._device
-            dev.sync()                               # library stream -> host
+            # NCCL orders itself after torch's current stream; if the library runs on that very stream the
+            # whole day stays stream-ordered, otherwise fence the two streams through the host
+            shared = dev.stream is not None and torch.cuda.current_stream(dev.index).cuda_stream == dev.stream
+            if not shared:
+                dev.sync()
             t = load_tensor(lead, dev.index)
             allreduce_u32_(t, group)
-            torch.cuda.current_stream(dev.index).synchronize()
+            if not shared:
+                torch.cuda.current_stream(dev.index).synchronize()
     for s in sims[1:]:
         s._sim.load_copy(lead)
     for s in sims:

@@ -27,6 +27,7 @@ class Device(object):
         h = C.c_void_p()
         check(self.lib.s4_ctx_create(self.index, C.c_void_p(stream) if stream else None, C.byref(h)))
         self._h = h
+        self.stream = int(stream) if stream else None      # None: library-owned stream
 
     def close(self):
         if getattr(self, "_h", None):

@@ -27,7 +27,9 @@ device_settings = {
     # S4_ROOT_ORIGIN (0): one tree per distinct origin, the reference's grouping (simulation.py:71).
     # S4_ROOT_GOAL (1) / S4_ROOT_AUTO (2): root the trees at the goals / at the smaller endpoint set --
     # legitimate because the graph is undirected; identical loads wherever the shortest path is unique.
-    "root_mode": 0,
+    # Default AUTO: same loads as the reference wherever shortest paths are unique, 30x fewer trees on the
+    # BASELINE workloads (goals are a 2 % node sample).  Set 0 for the reference's exact grouping.
+    "root_mode": 2,
     # Reproduce python-graph's per-orientation attribute lists: a street inserted as (u, v) with u > v
     # never shows a changed speed limit to the weight loop (streetnetwork.py:79-82 vs :113-125).
     "orientation_aliasing": True,
