@@ -61,6 +61,8 @@ struct Options {
     int root_mode = S4_ROOT_ORIGIN;
     int walk_tile = 8;
     int sssp_variant = 1;           // 0 = barrier per relaxation round, 1 = barrier-free ring
+    int preread = 1;                // read dist[head] before the atomic min
+    int dist_l1 = 0;                // let L1 serve the filtering reads of dist[]
 };
 
 // Lifetime: handles are reference counted (sim -> graph -> ctx), so the host may
@@ -233,7 +235,8 @@ static void option_slot(Options &o, const char *key, int *kind, void **raw)
         {"near_smem_entries", 1, &o.near_smem_entries}, {"queue_entries", 2, &o.queue_entries},
         {"batch_roots", 2, &o.batch_roots},         {"pool_bytes", 0, &o.pool_bytes},
         {"root_mode", 1, &o.root_mode},             {"walk_tile", 1, &o.walk_tile},
-        {"sssp_variant", 1, &o.sssp_variant},
+        {"sssp_variant", 1, &o.sssp_variant},       {"preread", 1, &o.preread},
+        {"dist_l1", 1, &o.dist_l1},
     };
     for (auto &it : items)
         if (strcmp(it.k, key) == 0) { *kind = it.kind; *raw = it.p; return; }
@@ -468,7 +471,7 @@ static int ensure_scratch(s4_graph *g, const SsspLaunch &L, int64_t slots_wanted
     const int64_t by_mem = (int64_t)((double)free_b * 0.6 / (8.0 * (double)V));
     slots = std::max<int64_t>(1, std::min(std::min(slots, by_mem), slots_wanted));
     if (slots > g->pool_slots || !g->pool.p) {
-        CU(g->pool.alloc((size_t)slots * (size_t)V));
+        CU(g->pool.alloc((size_t)slots * (size_t)((V + 3) & ~(int64_t)3)));
         g->pool_slots = slots;
     }
     int64_t q = o.queue_entries > 0 ? o.queue_entries : std::max<int64_t>(65536, V / 4);
@@ -491,6 +494,7 @@ static int launch_sssp(s4_graph *g, const SsspLaunch &L, const Arc *ell, const A
     p.row_ptr = g->row_ptr.p;
     p.arcs = arcs;
     p.dist_pool = g->pool.p;
+    p.slot_stride = (size_t)((g->V + 3) & ~3);
     p.roots = d_roots;
     p.n_roots = n_roots;
     p.V = (u32)g->V;
@@ -502,6 +506,8 @@ static int launch_sssp(s4_graph *g, const SsspLaunch &L, const Arc *ell, const A
     p.near_scap = L.scap;
     p.near_gcap = g->near_gcap;
     p.far_cap = g->far_cap;
+    p.preread = (u32)g->ctx->opt.preread;
+    p.dist_l1 = (u32)g->ctx->opt.dist_l1;
     p.counters = counters;
     const int grid = std::min(L.grid, std::max(1, n_roots));
     L.fn<<<grid, L.block, L.smem, g->ctx->stream>>>(p);
@@ -863,6 +869,7 @@ extern "C" int s4_sim_step(s4_sim *sim)
         wp.row_ptr = g->row_ptr.p;
         wp.arcs = sim->arcs.p;
         wp.dist_pool = g->pool.p;
+        wp.slot_stride = (size_t)((g->V + 3) & ~3);
         wp.roots = sim->roots.p;
         wp.trip_target = sim->trip_target.p;
         wp.trip_root = sim->trip_root.p;

@@ -57,6 +57,9 @@ struct __align__(16) Arc {
 };
 
 __device__ __forceinline__ u64 ld_dist(const u64 *p) { return __ldcg(p); }   // L2-coherent with the atomics
+// filtering read: distances only ever decrease, so a stale (larger) value from L1 is conservative --
+// it can cause a superfluous atomicMin or the expansion of a superseded entry, never a wrong result
+__device__ __forceinline__ u64 ld_dist_filter(const u64 *p, u32 via_l1) { return via_l1 ? __ldca(p) : __ldcg(p); }
 __device__ __forceinline__ u32 hi32(u64 x) { return (u32)(x >> 32); }
 
 __device__ __forceinline__ Arc ld_arc(const Arc *p)
@@ -184,7 +187,8 @@ struct SsspParams {
     const Arc *ell;         // V * kEllWidth
     const u32 *row_ptr;     // V+1  (overflow arcs, fallback sweeps)
     const Arc *arcs;        // A
-    u64 *dist_pool;         // n_roots slots of V words (slot i <-> roots[i])
+    u64 *dist_pool;         // n_roots slots of slot_stride words (slot i <-> roots[i]); 32-byte aligned slots
+    size_t slot_stride;     // V rounded up to a multiple of 4
     const int32_t *roots;   // roots of this batch
     int n_roots;
     u32 V;
@@ -196,8 +200,67 @@ struct SsspParams {
     u32 near_scap;          // entries per near queue in shared memory
     u32 near_gcap;          // spill entries per near queue in global memory
     u32 far_cap;            // entries per far pile
+    u32 preread;            // 1: read dist[head] first and only issue the atomic when it can win; 0: atomic straight away
+    u32 dist_l1;            // 1: the filtering reads of dist[] may be served by L1 (a stale, larger value only costs a wasted atomic)
     u64 *counters;
 };
+
+// 256-bit loads (LDG.E.256 on sm_100a): one L1 wavefront instead of two per 32 bytes
+__device__ __forceinline__ void ld_row_half(const Arc *p, Arc &x, Arc &y)
+{
+    u32 r0, r1, r2, r3, r4, r5, r6, r7;
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7) : "l"(p));
+    x.col = r0; x.street = r1; x.w = __hiloint2double((int)r3, (int)r2);
+    y.col = r4; y.street = r5; y.w = __hiloint2double((int)r7, (int)r6);
+}
+__device__ __forceinline__ void ld_dist_sector(const u64 *p, u64 (&s)[4])
+{
+    asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(s[0]), "=l"(s[1]), "=l"(s[2]), "=l"(s[3]) : "l"(p));
+}
+__device__ __forceinline__ u64 pick4(const u64 (&s)[4], u32 k)
+{
+    const u64 lo = (k & 1u) ? s[1] : s[0], hi = (k & 1u) ? s[3] : s[2];
+    return (k & 2u) ? hi : lo;
+}
+
+// Expansion of one frontier entry (u, du) by one thread.  Memory operations, in flight together:
+// the 64-byte ELL row as two 256-bit loads and the 32-byte sector of dist[] that holds u (stale check
+// plus every neighbour that shares the sector -- with a locality-preserving numbering about half of
+// them); then one 8-byte read per remaining neighbour; then atomicMin for the arcs that can win.
+// kind[j]: 0 nothing, 1 improved and inside the bucket, 2 improved and beyond it.  Returns false for a
+// superseded entry.  `ovf` reports a node with more than kEllWidth arcs.
+__device__ __forceinline__ bool expand_entry(const Arc *__restrict__ ell, u64 *dist, u32 u, u64 du, u32 thr_hi, u32 preread,
+                                             u32 (&kind)[kEllWidth], u32 (&pv)[kEllWidth], u64 (&pd)[kEllWidth], bool &ovf)
+{
+    Arc a[kEllWidth];
+    u64 sec[4];
+    const Arc *row = ell + (size_t)u * kEllWidth;
+    ld_row_half(row, a[0], a[1]);
+    ld_row_half(row + 2, a[2], a[3]);
+    ld_dist_sector(dist + (u & ~3u), sec);
+    if (pick4(sec, u & 3u) < du) return false;              // superseded by a later push
+    ovf = (a[0].col & kOvfBit) != 0u;
+    u64 old[kEllWidth];
+#pragma unroll
+    for (int j = 0; j < kEllWidth; ++j) {
+        pv[j] = a[j].col & ~kOvfBit;
+        pd[j] = (u64)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)du), a[j].w));
+        old[j] = kInfBits;
+        if (preread) {
+            if ((pv[j] >> 2) == (u >> 2)) old[j] = pick4(sec, pv[j] & 3u);
+            else old[j] = ld_dist(dist + pv[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < kEllWidth; ++j) {
+        if (pd[j] < old[j]) {                                // padding slots have pd == +inf
+            const u64 o2 = atomicMin(dist + pv[j], pd[j]);
+            if (pd[j] < o2) kind[j] = hi32(pd[j]) <= thr_hi ? 1u : 2u;
+        }
+    }
+    return true;
+}
 
 struct Queue {
     u32 *sv; u64 *sd;       // shared-memory part (scap entries)
@@ -291,19 +354,15 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 512 ? 1024 / BLOCK : 1)) sssp
         __syncthreads();
         const int ri = s_root_idx;
         if (ri >= p.n_roots) break;
-        u64 *dist = p.dist_pool + (size_t)ri * V;
+        u64 *dist = p.dist_pool + (size_t)ri * p.slot_stride;
         const u32 root = (u32)p.roots[ri];
 
         // ---- fill the slot with +inf (16-byte stores)
         {
-            const size_t base_addr = (size_t)ri * V;
-            const u32 head = (u32)(base_addr & 1u);        // slot starts on an odd word
-            if (head && tid == 0) dist[0] = kInfBits;
-            ulonglong2 *d2 = reinterpret_cast<ulonglong2 *>(dist + head);
-            const u32 n2 = (V - head) >> 1;
+            ulonglong2 *d2 = reinterpret_cast<ulonglong2 *>(dist);
+            const u32 n2 = (u32)(p.slot_stride >> 1);
             const ulonglong2 inf2 = make_ulonglong2(kInfBits, kInfBits);
             for (u32 i = tid; i < n2; i += BLOCK) d2[i] = inf2;
-            if (((V - head) & 1u) && tid == 0) dist[V - 1] = kInfBits;
         }
         if (tid == 0) {
             s_cnt[0] = 1u; s_cnt[1] = 0u; s_cnt[2] = 0u;
@@ -337,40 +396,17 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 512 ? 1024 / BLOCK : 1)) sssp
                     const u32 i = base + tid;
                     bool valid = i < n_s;
                     u32 u = 0;
-                    u64 du = 0, cur = 0;
-                    Arc a[kEllWidth];
-                    if (valid) {
-                        if (i < scap) { u = qc.sv[i]; du = qc.sd[i]; }
-                        else { u = qc.gv[i - scap]; du = qc.gd[i - scap]; }
-                        const Arc *row = p.ell + (size_t)u * kEllWidth;
-#pragma unroll
-                        for (int j = 0; j < kEllWidth; ++j) a[j] = ld_arc(row + j);
-                        cur = ld_dist(dist + u);
-                        if (cur < du) { valid = false; ++c_stale; }     // superseded by a later push
-                        else ++c_pop;
-                    }
+                    u64 du = 0;
                     u32 kind[kEllWidth], pv[kEllWidth];
                     u64 pd[kEllWidth];
 #pragma unroll
                     for (int j = 0; j < kEllWidth; ++j) { kind[j] = 0u; pv[j] = 0u; pd[j] = 0ull; }
                     bool ovf = false;
                     if (valid) {
-                        ovf = (a[0].col & kOvfBit) != 0u;
-                        u64 old[kEllWidth];
-#pragma unroll
-                        for (int j = 0; j < kEllWidth; ++j) {
-                            pv[j] = a[j].col & ~kOvfBit;
-                            pd[j] = (u64)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)du), a[j].w));
-                            old[j] = ld_dist(dist + pv[j]);
-                        }
-#pragma unroll
-                        for (int j = 0; j < kEllWidth; ++j) {
-                            if (pd[j] < old[j]) {
-                                const u64 o2 = atomicMin(dist + pv[j], pd[j]);
-                                if (pd[j] < o2) kind[j] = hi32(pd[j]) <= thr_hi ? 1u : 2u;
-                            }
-                        }
-                        c_relax += kEllWidth;
+                        if (i < scap) { u = qc.sv[i]; du = qc.sd[i]; }
+                        else { u = qc.gv[i - scap]; du = qc.gd[i - scap]; }
+                        valid = expand_entry(p.ell, dist, u, du, thr_hi, p.preread, kind, pv, pd, ovf);
+                        if (valid) { ++c_pop; c_relax += kEllWidth; } else ++c_stale;
                     }
                     warp_push<kEllWidth>(kind, pv, pd, lane, qn, &s_cnt[cn], scap, gcap, fv, fd, &s_far_cnt[f],
                                          &s_far_min[f], fcap, &s_overflow, c_push);
@@ -603,17 +639,13 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 512 ? 1024 / BLOCK : 1)) sssp
         __syncthreads();
         const int ri = s_root_idx;
         if (ri >= p.n_roots) break;
-        u64 *dist = p.dist_pool + (size_t)ri * V;
+        u64 *dist = p.dist_pool + (size_t)ri * p.slot_stride;
         const u32 root = (u32)p.roots[ri];
         {
-            const size_t base_addr = (size_t)ri * V;
-            const u32 head = (u32)(base_addr & 1u);
-            if (head && tid == 0) dist[0] = kInfBits;
-            ulonglong2 *d2 = reinterpret_cast<ulonglong2 *>(dist + head);
-            const u32 n2 = (V - head) >> 1;
+            ulonglong2 *d2 = reinterpret_cast<ulonglong2 *>(dist);
+            const u32 n2 = (u32)(p.slot_stride >> 1);
             const ulonglong2 inf2 = make_ulonglong2(kInfBits, kInfBits);
             for (u32 i = tid; i < n2; i += BLOCK) d2[i] = inf2;
-            if (((V - head) & 1u) && tid == 0) dist[V - 1] = kInfBits;
         }
         if (tid == 0) {
             s_head = 0u; s_tail = 1u; s_done = 0u;
@@ -653,43 +685,20 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 512 ? 1024 / BLOCK : 1)) sssp
                 ++c_round;
                 bool valid = lane < n;
                 u32 u = 0;
-                u64 du = 0, cur = 0;
-                Arc a[kEllWidth];
-                if (valid) {
-                    const u32 slot = (start + lane) & R.mask;
-                    while ((u = ld_vol(rv + slot)) == kSlotEmpty) { }           // reserved, being written
-                    __threadfence_block();
-                    du = *reinterpret_cast<volatile u64 *>(rd + slot);
-                    *reinterpret_cast<volatile u32 *>(rv + slot) = kSlotEmpty;  // recycle before `done` moves
-                    const Arc *row = p.ell + (size_t)u * kEllWidth;
-#pragma unroll
-                    for (int j = 0; j < kEllWidth; ++j) a[j] = ld_arc(row + j);
-                    cur = ld_dist(dist + u);
-                    if (cur < du) { valid = false; ++c_stale; }
-                    else ++c_pop;
-                }
+                u64 du = 0;
                 u32 kind[kEllWidth], pv[kEllWidth];
                 u64 pd[kEllWidth];
 #pragma unroll
                 for (int j = 0; j < kEllWidth; ++j) { kind[j] = 0u; pv[j] = 0u; pd[j] = 0ull; }
                 bool ovf = false;
                 if (valid) {
-                    ovf = (a[0].col & kOvfBit) != 0u;
-                    u64 old[kEllWidth];
-#pragma unroll
-                    for (int j = 0; j < kEllWidth; ++j) {
-                        pv[j] = a[j].col & ~kOvfBit;
-                        pd[j] = (u64)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)du), a[j].w));
-                        old[j] = ld_dist(dist + pv[j]);
-                    }
-#pragma unroll
-                    for (int j = 0; j < kEllWidth; ++j) {
-                        if (pd[j] < old[j]) {
-                            const u64 o2 = atomicMin(dist + pv[j], pd[j]);
-                            if (pd[j] < o2) kind[j] = hi32(pd[j]) <= thr_hi ? 1u : 2u;
-                        }
-                    }
-                    c_relax += kEllWidth;
+                    const u32 slot = (start + lane) & R.mask;
+                    while ((u = ld_vol(rv + slot)) == kSlotEmpty) { }           // reserved, being written
+                    __threadfence_block();
+                    du = *reinterpret_cast<volatile u64 *>(rd + slot);
+                    *reinterpret_cast<volatile u32 *>(rv + slot) = kSlotEmpty;  // recycle before `done` moves
+                    valid = expand_entry(p.ell, dist, u, du, thr_hi, p.preread, kind, pv, pd, ovf);
+                    if (valid) { ++c_pop; c_relax += kEllWidth; } else ++c_stale;
                 }
                 warp_push_async<kEllWidth>(kind, pv, pd, lane, R, fv, fd, &s_far_cnt[f], &s_far_min[f], fcap, &s_overflow, c_push);
                 if (__any_sync(0xffffffffu, ovf)) {
@@ -833,6 +842,7 @@ struct WalkParams {
     const u32 *row_ptr;
     const Arc *arcs;
     const u64 *dist_pool;
+    size_t slot_stride;
     const int32_t *roots;       // distinct roots (all of them)
     const int32_t *trip_target; // trips sorted by root
     const u32 *trip_root;       // index of the trip's root among the distinct roots
@@ -855,7 +865,7 @@ __global__ void __launch_bounds__(256) walk_kernel(WalkParams p)
     for (int64_t t = p.t0 + tile_id; t < p.t1; t += tiles_per_grid) {
         const u32 ri = p.trip_root[t];
         const u32 root = (u32)p.roots[ri];
-        const u64 *dist = p.dist_pool + (size_t)(ri - p.root0) * p.V;
+        const u64 *dist = p.dist_pool + (size_t)(ri - p.root0) * p.slot_stride;
         u32 cur = (u32)p.trip_target[t];
         u64 dv = ld_dist(dist + cur);
         ++c_trips;
