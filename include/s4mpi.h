@@ -95,7 +95,7 @@ int s4_ctx_create(int device, void *stream, s4_ctx **out);
 int s4_ctx_destroy(s4_ctx *ctx);
 int s4_ctx_sync(s4_ctx *ctx);
 /* Tunables (all have defaults): "delta_factor" (bucket width in mean arc
- * weights), "block_threads" (256|512|1024), "ctas_per_sm", "near_smem_entries", "queue_entries", "batch_roots",
+ * weights), "block_threads" (32|64|128|256|512|1024), "ctas_per_sm", "near_smem_entries", "queue_entries", "batch_roots",
  * "pool_bytes", "root_mode" (S4_ROOT_*), "walk_tile" (4|8|16|32),
  * "sssp_variant" (0 = barrier per relaxation round, 1 = barrier-free ring). */
 int s4_ctx_set_option(s4_ctx *ctx, const char *key, double value);
@@ -107,9 +107,14 @@ int s4_ctx_device_info(s4_ctx *ctx, char *name_out, int name_cap, int *sm_count,
 /* Street i joins u[i] and v[i] (either orientation, the graph is undirected:
  * streetnetwork.py:24,37), has length[i] metres and speed limit max_speed[i]
  * km/h (> 0).  Builds the symmetric CSR (2 arcs per street, arcs of a node in
- * street_index order) and uploads it. */
+ * street_index order) and uploads it.  node_rank (may be NULL) is a permutation
+ * of 0..V-1 giving every node its position in the device's internal numbering
+ * (the host passes the order along a space-filling curve over the node
+ * coordinates: neighbours then share cache sectors of the per-tree distance
+ * arrays).  It changes no result: all ids crossing this ABI and the lowest-id
+ * tie-break stay in the caller's numbering. */
 int s4_graph_upload(s4_ctx *ctx, int32_t V, int64_t S, const int32_t *u, const int32_t *v,
-                    const double *length, const int32_t *max_speed, s4_graph **out);
+                    const double *length, const int32_t *max_speed, const int32_t *node_rank, s4_graph **out);
 int s4_graph_free(s4_graph *g);
 int s4_graph_dims(s4_graph *g, int32_t *V, int64_t *S, int64_t *A);
 /* StreetNetwork.calculate_shortest_paths (streetnetwork.py:108-109) with

@@ -54,7 +54,7 @@ SIGNATURES = {
     "s4_ctx_set_option": (C.c_int, [_vp, C.c_char_p, C.c_double]),
     "s4_ctx_get_option": (C.c_int, [_vp, C.c_char_p, _f64p]),
     "s4_ctx_device_info": (C.c_int, [_vp, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_uint64)]),
-    "s4_graph_upload": (C.c_int, [_vp, C.c_int32, C.c_int64, _i32p, _i32p, _f64p, _i32p, C.POINTER(_vp)]),
+    "s4_graph_upload": (C.c_int, [_vp, C.c_int32, C.c_int64, _i32p, _i32p, _f64p, _i32p, _i32p, C.POINTER(_vp)]),
     "s4_graph_free": (C.c_int, [_vp]),
     "s4_graph_dims": (C.c_int, [_vp, C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "s4_graph_sssp": (C.c_int, [_vp, _f64p, C.c_int32, _f64p, _i32p]),

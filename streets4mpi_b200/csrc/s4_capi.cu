@@ -52,15 +52,15 @@ static int fail(int code, const char *fmt, ...)
 // ---------------------------------------------------------------------------
 struct Options {
     double delta_factor = 2.0;
-    int block_threads = 512;
-    int ctas_per_sm = 2;
-    int near_smem_entries = 4096;
+    int block_threads = 0;          // 0 = from the graph (mean frontier width ~ V / hop depth)
+    int ctas_per_sm = 0;            // 0 = as many CTAs as keep 1024 threads per SM
+    int near_smem_entries = 0;      // 0 = 4 entries per thread
     int64_t queue_entries = 0;      // 0 = auto (from V)
     int64_t batch_roots = 0;        // 0 = auto (from pool_bytes)
     double pool_bytes = 24.0e9;
     int root_mode = S4_ROOT_ORIGIN;
     int walk_tile = 8;
-    int sssp_variant = 1;           // 0 = barrier per relaxation round, 1 = barrier-free ring
+    int sssp_variant = 0;           // 0 = barrier per relaxation round, 1 = barrier-free ring
     int preread = 1;                // read dist[head] before the atomic min
     int dist_l1 = 0;                // let L1 serve the filtering reads of dist[]
 };
@@ -110,10 +110,13 @@ struct s4_graph {
     DevBuf<uint2> arc_cs;      // A  {head, street}
     DevBuf<uint2> ell_cs;      // V*4 {head | overflow flag, street}; padding {self, ~0}
     DevBuf<double> length;     // S
+    DevBuf<u32> orig;          // device number -> caller's dense id (empty = identity numbering)
+    std::vector<int32_t> rank; // caller's dense id -> device number (empty = identity)
     std::vector<int32_t> max_speed0;   // host copy of the uploaded limits
     // connected components (host): algorithmic arcs / nodes of a tree rooted at r
     std::vector<int32_t> comp_of;
     std::vector<int64_t> comp_arcs, comp_nodes;
+    int auto_block = 256;      // CTA width chosen from the graph's shape (see graph upload)
     // scratch shared by every simulation on this graph (sized lazily)
     DevBuf<u64> pool;          // slots * V
     int64_t pool_slots = 0;
@@ -126,6 +129,7 @@ struct s4_graph {
     DevBuf<Arc> arcs_tmp, ell_tmp;
     DevBuf<double> w_tmp;
     DevBuf<int32_t> pred_tmp;
+    DevBuf<double> dist_tmp;
     DevBuf<int32_t> root_tmp;
     DevBuf<u64> ctr_tmp;
     DevBuf<double> wsum_tmp;
@@ -256,9 +260,10 @@ extern "C" int s4_ctx_set_option(s4_ctx *ctx, const char *key, double value)
     else if (kind == 1) *(int *)raw = (int)value;
     else *(int64_t *)raw = (int64_t)value;
     const Options &t = trial;
-    bool ok = t.delta_factor >= 0.0 && (t.block_threads == 256 || t.block_threads == 512 || t.block_threads == 1024) &&
-              t.ctas_per_sm >= 1 && t.ctas_per_sm <= 8 &&
-              t.near_smem_entries >= 64 && t.near_smem_entries <= 9000 && t.queue_entries >= 0 &&
+    bool ok = t.delta_factor >= 0.0 && (t.block_threads == 0 || t.block_threads == 32 || t.block_threads == 64 || t.block_threads == 128 || t.block_threads == 256 ||
+               t.block_threads == 512 || t.block_threads == 1024) &&
+              t.ctas_per_sm >= 0 && t.ctas_per_sm <= 32 &&
+              (t.near_smem_entries == 0 || (t.near_smem_entries >= 32 && t.near_smem_entries <= 9000)) && t.queue_entries >= 0 &&
               t.batch_roots >= 0 && t.pool_bytes >= 0.0 && t.root_mode >= 0 && t.root_mode <= 2 &&
               (t.walk_tile == 4 || t.walk_tile == 8 || t.walk_tile == 16 || t.walk_tile == 32) &&
               (t.sssp_variant == 0 || t.sssp_variant == 1);
@@ -299,18 +304,37 @@ static int32_t uf_find(std::vector<int32_t> &parent, int32_t x)
     return x;
 }
 
-extern "C" int s4_graph_upload(s4_ctx *ctx, int32_t V, int64_t S, const int32_t *u, const int32_t *v,
-                               const double *length, const int32_t *max_speed, s4_graph **out)
+extern "C" int s4_graph_upload(s4_ctx *ctx, int32_t V, int64_t S, const int32_t *u_in, const int32_t *v_in,
+                               const double *length, const int32_t *max_speed, const int32_t *node_rank, s4_graph **out)
 {
     CHECK_ARG(ctx && out, "s4_graph_upload: NULL argument");
+    const int32_t *u = u_in, *v = v_in;
     *out = nullptr;
     CHECK_ARG(V > 0, "s4_graph_upload: V must be positive");
     CHECK_ARG(S >= 0 && S < (int64_t)1 << 31, "s4_graph_upload: S out of range");
     CHECK_ARG(S == 0 || (u && v && length && max_speed), "s4_graph_upload: NULL street array");
     CU(cudaSetDevice(ctx->device));
+    for (int64_t s = 0; s < S; ++s)
+        if (u[s] < 0 || u[s] >= V || v[s] < 0 || v[s] >= V) return fail(S4_ERR_ARG, "street %lld: node id out of range", (long long)s);
+    // optional device numbering (a permutation of 0..V-1, e.g. along a space-filling curve): everything
+    // below is built in device numbers; ids only matter for the tie-break, which consults `orig`
+    std::vector<int32_t> uu, vv;
+    std::vector<u32> orig_h;
+    if (node_rank) {
+        orig_h.assign((size_t)V, 0xFFFFFFFFu);
+        for (int32_t i = 0; i < V; ++i) {
+            const int32_t r = node_rank[i];
+            if (r < 0 || r >= V || orig_h[(size_t)r] != 0xFFFFFFFFu) return fail(S4_ERR_ARG, "node_rank is not a permutation of 0..V-1");
+            orig_h[(size_t)r] = (u32)i;
+        }
+        uu.resize((size_t)S);
+        vv.resize((size_t)S);
+        for (int64_t s = 0; s < S; ++s) { uu[(size_t)s] = node_rank[u[s]]; vv[(size_t)s] = node_rank[v[s]]; }
+        u = uu.data();
+        v = vv.data();
+    }
     std::vector<u32> row_ptr((size_t)V + 1, 0u);
     for (int64_t s = 0; s < S; ++s) {
-        if (u[s] < 0 || u[s] >= V || v[s] < 0 || v[s] >= V) return fail(S4_ERR_ARG, "street %lld: node id out of range", (long long)s);
         if (!(length[s] >= 0.0) || std::isinf(length[s])) return fail(S4_ERR_ARG, "street %lld: length must be finite and >= 0", (long long)s);
         if (max_speed[s] < 1) return fail(S4_ERR_ARG, "street %lld: max_speed must be >= 1", (long long)s);
         ++row_ptr[(size_t)u[s] + 1];
@@ -347,6 +371,7 @@ extern "C" int s4_graph_upload(s4_ctx *ctx, int32_t V, int64_t S, const int32_t 
     g->S = S;
     g->A = A;
     g->max_speed0.assign(max_speed, max_speed + S);
+    if (node_rank) g->rank.assign(node_rank, node_rank + V);
     // connected components -> algorithmic work of a tree (each arc of the
     // root's component is scanned exactly once by any exact SSSP)
     {
@@ -366,6 +391,42 @@ extern "C" int s4_graph_upload(s4_ctx *ctx, int32_t V, int64_t S, const int32_t 
             g->comp_arcs[(size_t)r] += row_ptr[(size_t)i + 1] - row_ptr[(size_t)i];
         }
     }
+    // Shape of a shortest-path wave on this graph: two BFS sweeps give the hop depth; V / depth is the mean
+    // number of nodes a tree has in flight per relaxation round.  Wide waves (grids: ~V^(1/2)) want a wide
+    // CTA per tree, long thin ones (chains of degree-2 nodes) want many small CTAs in flight instead.
+    {
+        std::vector<int32_t> level((size_t)V, -1), queue((size_t)V);
+        auto bfs = [&](int32_t src, int32_t *far_node, int64_t *reached) {
+            std::fill(level.begin(), level.end(), -1);
+            int64_t head = 0, tail = 0;
+            queue[(size_t)tail++] = src;
+            level[(size_t)src] = 0;
+            int32_t last = src;
+            while (head < tail) {
+                const int32_t x = queue[(size_t)head++];
+                last = x;
+                for (u32 e = row_ptr[(size_t)x]; e < row_ptr[(size_t)x + 1]; ++e) {
+                    const int32_t y = (int32_t)arc_cs[e].x;
+                    if (level[(size_t)y] < 0) { level[(size_t)y] = level[(size_t)x] + 1; queue[(size_t)tail++] = y; }
+                }
+            }
+            *far_node = last;
+            *reached = tail;
+            return level[(size_t)last];
+        };
+        int32_t start = 0;
+        int64_t best = 0;
+        for (int32_t i = 0; i < V; ++i)
+            if (g->comp_nodes[(size_t)i] > best) { best = g->comp_nodes[(size_t)i]; start = i; }   // root of the largest component
+        int32_t far1 = start, far2 = start;
+        int64_t reached = 1;
+        bfs(start, &far1, &reached);
+        const int32_t depth = std::max<int32_t>(1, bfs(far1, &far2, &reached));
+        const double width = (double)reached / (double)depth;
+        int blk = 32;
+        while (blk < 256 && (double)blk * 2.0 <= width) blk *= 2;
+        g->auto_block = blk;
+    }
     auto bail = [&](cudaError_t e, const char *what) {
         delete g;
         --ctx->refs;
@@ -376,6 +437,10 @@ extern "C" int s4_graph_upload(s4_ctx *ctx, int32_t V, int64_t S, const int32_t 
     if ((e = g->arc_cs.alloc((size_t)std::max<int64_t>(A, 1))) != cudaSuccess) return bail(e, "alloc arcs");
     if ((e = g->length.alloc((size_t)std::max<int64_t>(S, 1))) != cudaSuccess) return bail(e, "alloc length");
     if ((e = g->ell_cs.alloc((size_t)V * kEllWidth)) != cudaSuccess) return bail(e, "alloc ell");
+    if (node_rank) {
+        if ((e = g->orig.alloc((size_t)V)) != cudaSuccess) return bail(e, "alloc orig");
+        if ((e = cudaMemcpyAsync(g->orig.p, orig_h.data(), (size_t)V * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) return bail(e, "copy orig");
+    }
     if ((e = cudaMemcpyAsync(g->ell_cs.p, ell_cs.data(), (size_t)V * kEllWidth * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) return bail(e, "copy ell");
     if ((e = cudaMemcpyAsync(g->row_ptr.p, row_ptr.data(), ((size_t)V + 1) * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) return bail(e, "copy row_ptr");
     if (A > 0 && (e = cudaMemcpyAsync(g->arc_cs.p, arc_cs.data(), (size_t)A * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) return bail(e, "copy arcs");
@@ -419,6 +484,9 @@ typedef void (*SsspKernel)(SsspParams);
 static SsspKernel pick_sssp(int block, int variant)
 {
     switch (block) {
+        case 32: return variant ? sssp_async_kernel<32> : sssp_nearfar_kernel<32>;
+        case 64: return variant ? sssp_async_kernel<64> : sssp_nearfar_kernel<64>;
+        case 128: return variant ? sssp_async_kernel<128> : sssp_nearfar_kernel<128>;
         case 256: return variant ? sssp_async_kernel<256> : sssp_nearfar_kernel<256>;
         case 512: return variant ? sssp_async_kernel<512> : sssp_nearfar_kernel<512>;
         case 1024: return variant ? sssp_async_kernel<1024> : sssp_nearfar_kernel<1024>;
@@ -436,26 +504,29 @@ struct SsspLaunch {
 static int plan_sssp(s4_graph *g, SsspLaunch *L)
 {
     const Options &o = g->ctx->opt;
-    L->fn = pick_sssp(o.block_threads, o.sssp_variant);
-    if (!L->fn) return fail(S4_ERR_ARG, "no SSSP kernel for block=%d", o.block_threads);
-    L->block = o.block_threads;
+    const int block = o.block_threads ? o.block_threads : g->auto_block;
+    const int near_entries = o.near_smem_entries ? o.near_smem_entries : std::max(128, 4 * block);
+    const int ctas = o.ctas_per_sm ? o.ctas_per_sm : std::min(32, std::max(1, 1024 / block));
+    L->fn = pick_sssp(block, o.sssp_variant);
+    if (!L->fn) return fail(S4_ERR_ARG, "no SSSP kernel for block=%d", block);
+    L->block = block;
     if (o.sssp_variant) {
-        // one ring of 2 * near_smem_entries slots rounded down to a power of two (same shared-memory budget),
+        // one ring of 2 * near_entries slots rounded down to a power of two (same shared-memory budget),
         // never smaller than twice the worst-case concurrent push of the CTA
-        u32 want = (u32)o.near_smem_entries * 2u, rcap = 1u;
+        u32 want = (u32)near_entries * 2u, rcap = 1u;
         while (rcap * 2u <= want) rcap *= 2u;
-        while (rcap < (u32)o.block_threads * kEllWidth * 2u) rcap *= 2u;
+        while (rcap < (u32)block * kEllWidth * 2u) rcap *= 2u;
         L->scap = rcap;
         L->smem = (size_t)rcap * (sizeof(u64) + sizeof(u32));
     } else {
-        L->scap = (u32)o.near_smem_entries;
+        L->scap = (u32)near_entries;
         L->smem = (size_t)2 * L->scap * (sizeof(u64) + sizeof(u32));
     }
     CU(cudaFuncSetAttribute((const void *)L->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L->smem));
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)L->fn, L->block, L->smem));
     if (occ < 1) return fail(S4_ERR_ARG, "SSSP kernel does not fit on an SM (block=%d, smem=%zu)", L->block, L->smem);
-    L->grid = g->ctx->prop.multiProcessorCount * std::min(occ, o.ctas_per_sm);
+    L->grid = g->ctx->prop.multiProcessorCount * std::min(occ, ctas);
     return S4_OK;
 }
 
@@ -474,7 +545,10 @@ static int ensure_scratch(s4_graph *g, const SsspLaunch &L, int64_t slots_wanted
         CU(g->pool.alloc((size_t)slots * (size_t)((V + 3) & ~(int64_t)3)));
         g->pool_slots = slots;
     }
-    int64_t q = o.queue_entries > 0 ? o.queue_entries : std::max<int64_t>(65536, V / 4);
+    // per-CTA spill / far-pile capacity: a quarter of the nodes for a 256-wide CTA, proportionally less for
+    // the narrow CTAs used on thin-wave graphs (an overflow is survivable: Bellman-Ford safety net)
+    int64_t q = o.queue_entries > 0 ? o.queue_entries
+                                    : std::max<int64_t>(8192, std::max<int64_t>(65536, V / 4) * std::min(L.block, 256) / 256);
     q = std::min<int64_t>(q, std::max<int64_t>(V, 1024) * 2);
     if (L.grid > g->ws_ctas || (u32)q != g->near_gcap || !g->ws_v.p) {
         CU(g->ws_v.alloc((size_t)L.grid * 4 * (size_t)q));
@@ -515,17 +589,17 @@ static int launch_sssp(s4_graph *g, const SsspLaunch &L, const Arc *ell, const A
     return S4_OK;
 }
 
-static int launch_pred(s4_graph *g, const Arc *arcs, const u64 *dist, u32 root, int32_t *pred)
+static int launch_pred(s4_graph *g, const Arc *arcs, const u64 *dist, u32 root, int32_t *pred, double *dist_out)
 {
     const int tile = g->ctx->opt.walk_tile;
     const int block = 256;
     const int grid = grid_for((int64_t)g->V * tile, block, g->ctx);
     cudaStream_t st = g->ctx->stream;
     switch (tile) {
-        case 4: pred_kernel<4><<<grid, block, 0, st>>>(g->row_ptr.p, arcs, dist, (u32)g->V, root, pred); break;
-        case 8: pred_kernel<8><<<grid, block, 0, st>>>(g->row_ptr.p, arcs, dist, (u32)g->V, root, pred); break;
-        case 16: pred_kernel<16><<<grid, block, 0, st>>>(g->row_ptr.p, arcs, dist, (u32)g->V, root, pred); break;
-        default: pred_kernel<32><<<grid, block, 0, st>>>(g->row_ptr.p, arcs, dist, (u32)g->V, root, pred); break;
+        case 4: pred_kernel<4><<<grid, block, 0, st>>>(g->row_ptr.p, arcs, g->orig.p, dist, (u32)g->V, root, pred, dist_out); break;
+        case 8: pred_kernel<8><<<grid, block, 0, st>>>(g->row_ptr.p, arcs, g->orig.p, dist, (u32)g->V, root, pred, dist_out); break;
+        case 16: pred_kernel<16><<<grid, block, 0, st>>>(g->row_ptr.p, arcs, g->orig.p, dist, (u32)g->V, root, pred, dist_out); break;
+        default: pred_kernel<32><<<grid, block, 0, st>>>(g->row_ptr.p, arcs, g->orig.p, dist, (u32)g->V, root, pred, dist_out); break;
     }
     CU(cudaGetLastError());
     return S4_OK;
@@ -564,6 +638,8 @@ extern "C" int s4_graph_sssp(s4_graph *g, const double *w_street, int32_t origin
     CU(g->ell_tmp.ensure((size_t)g->V * kEllWidth));
     CU(g->w_tmp.ensure((size_t)std::max<int64_t>(g->S, 1)));
     CU(g->pred_tmp.ensure((size_t)g->V));
+    CU(g->dist_tmp.ensure((size_t)g->V));
+    const int32_t origin_dev = g->rank.empty() ? origin : g->rank[(size_t)origin];
     CU(g->root_tmp.ensure(1));
     CU(g->ctr_tmp.ensure(C_COUNT));
     CU(g->wsum_tmp.ensure(1));
@@ -573,7 +649,7 @@ extern "C" int s4_graph_sssp(s4_graph *g, const double *w_street, int32_t origin
     for (int64_t s = 0; s < g->S; ++s) wsum += w_street[s];
     if (g->S > 0) CU(cudaMemcpyAsync(g->w_tmp.p, w_street, (size_t)g->S * sizeof(double), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(g->wsum_tmp.p, &wsum, sizeof(double), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(g->root_tmp.p, &origin, sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(g->root_tmp.p, &origin_dev, sizeof(int32_t), cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(g->ctr_tmp.p, 0, C_COUNT * sizeof(u64), st));
     CU(cudaMemsetAsync(g->work_counters.p, 0, sizeof(u32), st));
     if (g->A > 0) {
@@ -585,12 +661,11 @@ extern "C" int s4_graph_sssp(s4_graph *g, const double *w_street, int32_t origin
     CU(cudaGetLastError());
     rc = launch_sssp(g, L, g->ell_tmp.p, g->arcs_tmp.p, g->root_tmp.p, 1, g->work_counters.p, g->wsum_tmp.p, g->ctr_tmp.p);
     if (rc) return rc;
-    if (pred_out) {
-        rc = launch_pred(g, g->arcs_tmp.p, g->pool.p, (u32)origin, g->pred_tmp.p);
-        if (rc) return rc;
-        CU(cudaMemcpyAsync(pred_out, g->pred_tmp.p, (size_t)g->V * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    }
-    if (dist_out) CU(cudaMemcpyAsync(dist_out, g->pool.p, (size_t)g->V * sizeof(double), cudaMemcpyDeviceToHost, st));
+    // predecessors and distances come back in the caller's numbering
+    rc = launch_pred(g, g->arcs_tmp.p, g->pool.p, (u32)origin_dev, g->pred_tmp.p, g->dist_tmp.p);
+    if (rc) return rc;
+    if (pred_out) CU(cudaMemcpyAsync(pred_out, g->pred_tmp.p, (size_t)g->V * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (dist_out) CU(cudaMemcpyAsync(dist_out, g->dist_tmp.p, (size_t)g->V * sizeof(double), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     return S4_OK;
 }
@@ -644,6 +719,14 @@ extern "C" int s4_sim_create(s4_graph *g, int64_t T, const int32_t *origin, cons
     sim->root_mode = mode;
     const int32_t *root_h = mode == S4_ROOT_GOAL ? goal : origin;
     const int32_t *target_h = mode == S4_ROOT_GOAL ? origin : goal;
+    std::vector<int32_t> root_m, target_m;
+    if (!g->rank.empty() && T > 0) {
+        root_m.resize((size_t)T);
+        target_m.resize((size_t)T);
+        for (int64_t i = 0; i < T; ++i) { root_m[(size_t)i] = g->rank[(size_t)root_h[i]]; target_m[(size_t)i] = g->rank[(size_t)target_h[i]]; }
+        root_h = root_m.data();
+        target_h = target_m.data();
+    }
     cudaStream_t st = ctx->stream;
     const int64_t S = g->S, A = g->A;
 
@@ -868,6 +951,7 @@ extern "C" int s4_sim_step(s4_sim *sim)
         WalkParams wp;
         wp.row_ptr = g->row_ptr.p;
         wp.arcs = sim->arcs.p;
+        wp.orig = g->orig.p;
         wp.dist_pool = g->pool.p;
         wp.slot_stride = (size_t)((g->V + 3) & ~3);
         wp.roots = sim->roots.p;

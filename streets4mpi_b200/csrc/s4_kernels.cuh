@@ -316,7 +316,7 @@ __device__ __forceinline__ void warp_push(const u32 (&kind)[N], const u32 (&pv)[
 }
 
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK, (BLOCK <= 512 ? 1024 / BLOCK : 1)) sssp_nearfar_kernel(SsspParams p)
+__global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024 / BLOCK : 1)) sssp_nearfar_kernel(SsspParams p)
 {
     static_assert(BLOCK % 32 == 0, "whole warps");
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -601,7 +601,7 @@ __device__ __forceinline__ void warp_push_async(u32 (&kind)[N], const u32 (&pv)[
 }
 
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK, (BLOCK <= 512 ? 1024 / BLOCK : 1)) sssp_async_kernel(SsspParams p)
+__global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024 / BLOCK : 1)) sssp_async_kernel(SsspParams p)
 {
     static_assert(BLOCK % 32 == 0, "whole warps");
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -794,18 +794,23 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 512 ? 1024 / BLOCK : 1)) sssp
 // ---------------------------------------------------------------------------
 // Canonical predecessor of `cur` from converged distances, evaluated by the
 // lanes of one tile (lane k looks at arcs rb+k, rb+k+TILE, ...):
-//   min (u, street) over arcs (cur,u), u != cur, with fl(dist[u]+w) == dist[cur]
-//   and (dist[u] < dist[cur] or u < cur); if empty, over all equal-cost arcs.
-// Returns the packed key (u << 32 | street), ~0 if there is none; *du_out is
-// dist[u] of the winner (valid on every lane of the tile).
+//   min (id(u), street) over arcs (cur,u), u != cur, with fl(dist[u]+w) == dist[cur]
+//   and (dist[u] < dist[cur] or id(u) < id(cur)); if empty, over all equal-cost arcs.
+// id() is the caller's node id: the device numbers nodes along a space-filling
+// curve (locality), `orig` maps that numbering back so that the tie-break is the
+// one the host sees (nullptr = identical numbering).
+// Returns the packed key (id(u) << 32 | street), ~0 if there is none; *col_out is
+// the device number of the winner and *du_out its distance (valid on every lane).
 // ---------------------------------------------------------------------------
 template <int TILE>
 __device__ __forceinline__ u64 canonical_pred(const cg::thread_block_tile<TILE> &tile, const u32 *__restrict__ row_ptr,
-                                              const Arc *__restrict__ arcs, const u64 *dist, u32 cur, u64 dv,
-                                              u64 *du_out)
+                                              const Arc *__restrict__ arcs, const u32 *__restrict__ orig, const u64 *dist,
+                                              u32 cur, u64 dv, u32 *col_out, u64 *du_out)
 {
     const u32 rb = __ldg(row_ptr + cur), re = __ldg(row_ptr + cur + 1);
+    const u32 id_cur = orig ? __ldg(orig + cur) : cur;
     u64 strict = ~0ull, loose = ~0ull, du_s = 0, du_l = 0;
+    u32 col_s = 0, col_l = 0;
     for (u32 e = rb + tile.thread_rank(); tile.any(e < re); e += TILE) {
         if (e < re) {
             const Arc a = ld_arc(arcs + e);
@@ -813,22 +818,26 @@ __device__ __forceinline__ u64 canonical_pred(const cg::thread_block_tile<TILE> 
                 const u64 du = ld_dist(dist + a.col);
                 const u64 ndb = (u64)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)du), a.w));
                 if (du < kInfBits && ndb == dv) {
-                    const u64 key = ((u64)a.col << 32) | a.street;
-                    if (key < loose) { loose = key; du_l = du; }
-                    if ((du < dv || a.col < cur) && key < strict) { strict = key; du_s = du; }
+                    const u32 id_u = orig ? __ldg(orig + a.col) : a.col;
+                    const u64 key = ((u64)id_u << 32) | a.street;
+                    if (key < loose) { loose = key; du_l = du; col_l = a.col; }
+                    if ((du < dv || id_u < id_cur) && key < strict) { strict = key; du_s = du; col_s = a.col; }
                 }
             }
         }
     }
-    // tile-wide minimum of both keys, carrying the winner's distance along
+    // tile-wide minimum of both keys, carrying the winner's number and distance along
     for (int o = TILE / 2; o > 0; o >>= 1) {
         const u64 ks = tile.shfl_xor(strict, o), ds = tile.shfl_xor(du_s, o);
-        if (ks < strict) { strict = ks; du_s = ds; }
+        const u32 cs = tile.shfl_xor(col_s, o);
+        if (ks < strict) { strict = ks; du_s = ds; col_s = cs; }
         const u64 kl = tile.shfl_xor(loose, o), dl = tile.shfl_xor(du_l, o);
-        if (kl < loose) { loose = kl; du_l = dl; }
+        const u32 cl = tile.shfl_xor(col_l, o);
+        if (kl < loose) { loose = kl; du_l = dl; col_l = cl; }
     }
-    if (strict != ~0ull) { *du_out = du_s; return strict; }
+    if (strict != ~0ull) { *du_out = du_s; *col_out = col_s; return strict; }
     *du_out = du_l;
+    *col_out = col_l;
     return loose;
 }
 
@@ -841,10 +850,11 @@ __device__ __forceinline__ u64 canonical_pred(const cg::thread_block_tile<TILE> 
 struct WalkParams {
     const u32 *row_ptr;
     const Arc *arcs;
+    const u32 *orig;            // device number -> caller's node id (nullptr = identity)
     const u64 *dist_pool;
     size_t slot_stride;
-    const int32_t *roots;       // distinct roots (all of them)
-    const int32_t *trip_target; // trips sorted by root
+    const int32_t *roots;       // distinct roots (all of them), device numbers
+    const int32_t *trip_target; // trips sorted by root, device numbers
     const u32 *trip_root;       // index of the trip's root among the distinct roots
     int64_t t0, t1;             // trips of this batch
     u32 root0;                  // first root of this batch (slot = trip_root - root0)
@@ -873,11 +883,12 @@ __global__ void __launch_bounds__(256) walk_kernel(WalkParams p)
         u32 guard = 0;
         while (cur != root) {                                              // :83
             u64 du;
-            const u64 key = canonical_pred<TILE>(tile, p.row_ptr, p.arcs, dist, cur, dv, &du);
+            u32 nxt;
+            const u64 key = canonical_pred<TILE>(tile, p.row_ptr, p.arcs, p.orig, dist, cur, dv, &nxt, &du);
             if (key == ~0ull || ++guard > p.V) { ++c_stuck; break; }
             if (tile.thread_rank() == 0) atomicAdd(p.load + (u32)key, p.volume);   // :86-88
             ++c_hops;
-            cur = (u32)(key >> 32);                                        // :85
+            cur = nxt;                                                     // :85
             dv = du;
         }
     }
@@ -889,10 +900,11 @@ __global__ void __launch_bounds__(256) walk_kernel(WalkParams p)
     }
 }
 
-// predecessor map of one tree (StreetNetwork.calculate_shortest_paths, streetnetwork.py:108-109)
+// predecessor map and distances of one tree in the caller's numbering
+// (StreetNetwork.calculate_shortest_paths, streetnetwork.py:108-109)
 template <int TILE>
-__global__ void __launch_bounds__(256) pred_kernel(const u32 *row_ptr, const Arc *arcs, const u64 *dist, u32 V,
-                                                   u32 root, int32_t *pred)
+__global__ void __launch_bounds__(256) pred_kernel(const u32 *row_ptr, const Arc *arcs, const u32 *orig, const u64 *dist,
+                                                   u32 V, u32 root, int32_t *pred_out, double *dist_out)
 {
     cg::thread_block block = cg::this_thread_block();
     cg::thread_block_tile<TILE> tile = cg::tiled_partition<TILE>(block);
@@ -902,10 +914,15 @@ __global__ void __launch_bounds__(256) pred_kernel(const u32 *row_ptr, const Arc
         int32_t pr = -1;
         if (v != root && dv < kInfBits) {
             u64 du;
-            const u64 key = canonical_pred<TILE>(tile, row_ptr, arcs, dist, v, dv, &du);
+            u32 nxt;
+            const u64 key = canonical_pred<TILE>(tile, row_ptr, arcs, orig, dist, v, dv, &nxt, &du);
             if (key != ~0ull) pr = (int32_t)(key >> 32);
         }
-        if (tile.thread_rank() == 0) pred[v] = pr;
+        if (tile.thread_rank() == 0) {
+            const u32 id_v = orig ? orig[v] : v;
+            pred_out[id_v] = pr;
+            dist_out[id_v] = __longlong_as_double((long long)dv);
+        }
     }
 }
 

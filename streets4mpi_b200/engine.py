@@ -89,7 +89,8 @@ def make_physics(settings):
 class DeviceGraph(object):
     """Symmetric CSR of the street network in HBM (s4_graph)."""
 
-    def __init__(self, device, V, u, v, length, max_speed):
+    def __init__(self, device, V, u, v, length, max_speed, node_rank=None):
+        """node_rank: optional permutation, position of every node in the device's internal numbering."""
         self.device = device
         self.lib = device.lib
         u = as_array(u, np.int32)
@@ -99,8 +100,12 @@ class DeviceGraph(object):
         if not (len(u) == len(v) == len(length) == len(max_speed)):
             raise ValueError("street arrays differ in length")
         h = C.c_void_p()
+        rank = None if node_rank is None else as_array(node_rank, np.int32)
+        if rank is not None and len(rank) != int(V):
+            raise ValueError("node_rank must have one entry per node")
         check(self.lib.s4_graph_upload(device._h, int(V), len(u), ptr(u, C.c_int32), ptr(v, C.c_int32),
-                                       ptr(length, C.c_double), ptr(max_speed, C.c_int32), C.byref(h)))
+                                       ptr(length, C.c_double), ptr(max_speed, C.c_int32),
+                                       None if rank is None else ptr(rank, C.c_int32), C.byref(h)))
         self._h = h
         self.V, self.S = int(V), len(u)
         a = C.c_int64()

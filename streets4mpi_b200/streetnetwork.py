@@ -76,7 +76,8 @@ class _UndirectedGraph(object):
 
 class FlatNetwork(object):
     """Dense-array view of a StreetNetwork (what crosses the C-ABI)."""
-    __slots__ = ("node_ids", "u", "v", "length", "max_speed", "max_speed_insertion", "adaptable", "driving_time")
+    __slots__ = ("node_ids", "u", "v", "length", "max_speed", "max_speed_insertion", "adaptable", "driving_time",
+                 "lon", "lat")
 
     @property
     def V(self):
@@ -85,6 +86,33 @@ class FlatNetwork(object):
     @property
     def S(self):
         return len(self.u)
+
+    def locality_rank(self):
+        """Position of every node along a Z-order (Morton) curve over the rank-quantised coordinates,
+        or None when the coordinates carry no information.  Pure memory-layout hint for the device
+        (neighbouring nodes share cache sectors); no result depends on it."""
+        if self.lon is None or self.lat is None or len(self.node_ids) < 8:
+            return None
+        if np.ptp(self.lon) == 0 and np.ptp(self.lat) == 0:
+            return None
+        n = len(self.node_ids)
+
+        def quantise(x):
+            r = np.empty(n, dtype=np.uint64)
+            r[np.argsort(x, kind="stable")] = np.arange(n, dtype=np.uint64)
+            return (r * np.uint64(65536)) // np.uint64(n)
+
+        def spread(x):
+            x = (x | (x << np.uint64(8))) & np.uint64(0x00FF00FF)
+            x = (x | (x << np.uint64(4))) & np.uint64(0x0F0F0F0F)
+            x = (x | (x << np.uint64(2))) & np.uint64(0x33333333)
+            x = (x | (x << np.uint64(1))) & np.uint64(0x55555555)
+            return x
+
+        key = spread(quantise(self.lon)) | (spread(quantise(self.lat)) << np.uint64(1))
+        rank = np.empty(n, dtype=np.int32)
+        rank[np.argsort(key, kind="stable")] = np.arange(n, dtype=np.int32)
+        return rank
 
     def dense(self, nodes):
         """original node ids -> dense ids (rank in ascending id order)"""
@@ -267,6 +295,9 @@ class StreetNetwork(object):
             f.length, f.max_speed = a["length"], a["max_speed"]
             f.max_speed_insertion, f.driving_time = a["max_speed_insertion"], a["driving_time"]
             f.adaptable = (a["u"] <= a["v"]).astype(np.uint8)
+            order = np.argsort(a["node_ids"], kind="stable")
+            f.lon = None if a["lon"] is None else a["lon"][order]
+            f.lat = None if a["lat"] is None else a["lat"][order]
         else:
             g = self._g
             ids = np.array(sorted(g.node_neighbors.keys()), dtype=np.int64)
@@ -289,6 +320,10 @@ class StreetNetwork(object):
             f.u = np.searchsorted(ids, u).astype(np.int32)
             f.v = np.searchsorted(ids, v).astype(np.int32)
             f.adaptable = (u <= v).astype(np.uint8)
+            coords = [g.node_attr[n] for n in ids.tolist()]
+            ok = all(isinstance(c, (list, tuple)) and len(c) >= 2 for c in coords)
+            f.lon = np.array([c[0] for c in coords], dtype=np.float64) if ok else None
+            f.lat = np.array([c[1] for c in coords], dtype=np.float64) if ok else None
         self._flat_cache = (key, f)
         return f
 
@@ -300,7 +335,7 @@ class StreetNetwork(object):
         if cached is not None and cached[0] == self._topology_version and cached[1] is device:
             return cached[2]
         f = self.flat()
-        dg = engine.DeviceGraph(device, f.V, f.u, f.v, f.length, f.max_speed)
+        dg = engine.DeviceGraph(device, f.V, f.u, f.v, f.length, f.max_speed, node_rank=f.locality_rank())
         self._device_graph = (self._topology_version, device, dg)
         return dg
 

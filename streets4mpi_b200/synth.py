@@ -33,7 +33,9 @@ def grid_arrays(rows, cols, seed=1, arterial_every=64):
         v_col = (vu % cols) % arterial_every == arterial_every // 2
         art = np.concatenate([h_row, v_col])
         ms[art] = rng.choice(np.array([100, 120, 140], dtype=np.int32), size=int(art.sum()))
-    return {"node_ids": idx.ravel(), "u": u, "v": v, "length": length, "max_speed": ms}
+    rr, cc = np.divmod(idx.ravel(), cols)
+    return {"node_ids": idx.ravel(), "u": u, "v": v, "length": length, "max_speed": ms,
+            "lon": cc.astype(np.float64), "lat": rr.astype(np.float64)}
 
 
 def planar_arrays(n_nodes, seed=1, mean_degree=2.4, extent=None):

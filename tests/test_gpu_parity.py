@@ -147,7 +147,8 @@ def test_road_construction_golden(dev, phys):
                                   dict(block_threads=1024, delta_factor=8.0, near_smem_entries=64),
                                   dict(delta_factor=0.0), dict(sssp_variant=0), dict(sssp_variant=0, near_smem_entries=64),
                                   dict(sssp_variant=1, block_threads=256, near_smem_entries=64)])
-def test_sssp_dist_and_pred_vs_oracle(dev, shape, opts):
+@pytest.mark.parametrize("ranked", [False, True])
+def test_sssp_dist_and_pred_vs_oracle(dev, shape, opts, ranked):
     """Single trees: distances bit-equal to Dijkstra, predecessors equal under the canonical rule;
     kernel variants and bucket widths (incl. the tiny shared-memory queue that forces spills)."""
     from oracle import ctwin
@@ -156,7 +157,9 @@ def test_sssp_dist_and_pred_vs_oracle(dev, shape, opts):
     V = len(arr["node_ids"])
     rng = np.random.default_rng(1)
     w = rng.uniform(0.05, 13.0, size=len(arr["u"]))
-    g = engine.DeviceGraph(dev, V, arr["u"], arr["v"], arr["length"], arr["max_speed"])
+    rank = synth.network_from(arr).flat().locality_rank() if ranked else None      # device numbering along a Z curve
+    assert (rank is not None) == ranked
+    g = engine.DeviceGraph(dev, V, arr["u"], arr["v"], arr["length"], arr["max_speed"], node_rank=rank)
     csr = ctwin.Csr(V, arr["u"], arr["v"])
     defaults = {k: dev.get_option(k) for k in opts}
     try:
@@ -184,8 +187,11 @@ def test_ties_zero_weights_and_components(dev):
     v = np.concatenate([arr["v"], [401, 401, 7]]).astype(np.int32)
     S = len(u)
     rng = np.random.default_rng(2)
-    for w in (np.ones(S), rng.integers(0, 3, S).astype(np.float64), rng.integers(1, 4, S).astype(np.float64)):
-        g = engine.DeviceGraph(dev, V, u, v, np.full(S, 10.0), np.full(S, 50, dtype=np.int32))
+    for k, w in enumerate((np.ones(S), rng.integers(0, 3, S).astype(np.float64), rng.integers(1, 4, S).astype(np.float64),
+                           np.ones(S), rng.integers(0, 3, S).astype(np.float64))):
+        # the last two run on a shuffled device numbering: ties must still break on the caller's ids
+        rank = rng.permutation(V).astype(np.int32) if k >= 3 else None
+        g = engine.DeviceGraph(dev, V, u, v, np.full(S, 10.0), np.full(S, 50, dtype=np.int32), node_rank=rank)
         csr = ctwin.Csr(V, u, v)
         for src in (0, 210, 400, 404):
             dist, pred = g.sssp(w, src)
@@ -195,7 +201,8 @@ def test_ties_zero_weights_and_components(dev):
         g.close()
 
 
-def test_day_with_ties_matches_oracle(dev, phys):
+@pytest.mark.parametrize("ranked", [False, True])
+def test_day_with_ties_matches_oracle(dev, phys, ranked):
     """Equal lengths and speeds on a grid: every trip has many shortest paths; the CUDA walk
     and the oracle apply the same lowest-predecessor rule, so loads still agree bit for bit."""
     from oracle import ctwin
@@ -210,7 +217,8 @@ def test_day_with_ties_matches_oracle(dev, phys):
     rng = np.random.default_rng(3)
     o = rng.integers(0, rows * cols, 3000).astype(np.int32)
     gl = rng.integers(0, rows * cols, 3000).astype(np.int32)
-    g = engine.DeviceGraph(dev, rows * cols, u, v, L, ms)
+    rank = rng.permutation(rows * cols).astype(np.int32) if ranked else None
+    g = engine.DeviceGraph(dev, rows * cols, u, v, L, ms, node_rank=rank)
     sim = engine.DeviceSim(g, o, gl, 0.5, phys)
     csr = ctwin.Csr(rows * cols, u, v)
     prev = np.zeros(S, dtype=np.uint32)
@@ -324,6 +332,8 @@ def test_c_abi_error_behaviour(dev, phys):
         engine.DeviceGraph(dev, 4, [0, 9], [1, 2], [1.0, 1.0], [50, 50])          # node id out of range
     with pytest.raises(_ffi.S4Error):
         engine.DeviceGraph(dev, 4, [0], [1], [1.0], [0])                           # max_speed 0
+    with pytest.raises(_ffi.S4Error):
+        engine.DeviceGraph(dev, 4, [0], [1], [1.0], [50], node_rank=[0, 1, 1, 3])  # not a permutation
     g = engine.DeviceGraph(dev, 4, [0, 1], [1, 2], [10.0, 20.0], [50, 50])
     with pytest.raises(_ffi.S4Error):
         engine.DeviceSim(g, [0], [7], 0.1, phys)                                   # goal out of range

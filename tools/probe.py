@@ -18,6 +18,7 @@ ap.add_argument("--roots", type=int, default=1184)
 ap.add_argument("--configs", type=str, default="")
 ap.add_argument("--days", type=int, default=2)
 ap.add_argument("--morton", type=int, default=0)
+ap.add_argument("--rank", type=int, default=1)
 args = ap.parse_args()
 
 dev = engine.default_device()
@@ -44,7 +45,8 @@ rng = np.random.default_rng(0)
 origins = rng.choice(arr["node_ids"], size=args.roots, replace=False)
 goals = cats["goals"][rng.integers(0, len(cats["goals"]), size=args.roots)]
 phys = engine.make_physics(settings)
-g = engine.DeviceGraph(dev, V, arr["u"], arr["v"], arr["length"], arr["max_speed"])
+rank = synth.network_from(arr).flat().locality_rank() if args.rank else None
+g = engine.DeviceGraph(dev, V, arr["u"], arr["v"], arr["length"], arr["max_speed"], node_rank=rank)
 print("graph V=%d S=%d A=%d" % (V, g.S, g.A), flush=True)
 configs = [dict()]
 if args.configs:
