@@ -354,9 +354,12 @@ def gpu_arm(args):
 
     if rank == 0:
         peak, peak_src = measured_peak()
+        # The two lanes of a day run SSSP launches concurrently, so per-launch event times overlap; the
+        # kernel's time is taken as the union of its launches, bounded above by the whole timed region
+        # (it is >93 % of it, see profiles/): achieved = algorithmic bytes / launch, launch = region / launches.
         alg_bytes = 20.0 * c["arcs_algorithmic"] + 20.0 * c["nodes_algorithmic"]          # rank 0's launches
         n_launch = max(1, c["sssp_launches"])
-        ms_launch = c["ms_sssp"] / n_launch
+        ms_launch = min(c["ms_sssp"], ms) / n_launch
         achieved = alg_bytes / n_launch / (ms_launch * 1e-3) / 1e9 if ms_launch > 0 else 0.0
         traffic = None
         prof = os.path.join(ROOT, "profiles", "sssp_dram_bytes_per_tree.json")
@@ -377,8 +380,7 @@ def gpu_arm(args):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload + ": " + workload_text(args.workload),
                        "root_mode": "%s (trees per day and GPU: %d)" % (mode, sim._sim.n_roots),
-                       "virtual_ranks": world, "l2": "inputs larger than L2 (distance pool %.1f GB per GPU)"
-                       % (min(sim._sim.n_roots, 3000) * 8.0 * len(arrays["node_ids"]) / 1e9),
+                       "virtual_ranks": world, "l2": "inputs larger than L2 (per-tree distance arrays, 8 B x V x trees in flight >> 126 MB)",
                        "options": args.options or "defaults"},
             "gteps": arcs_alg / (ms_max * 1e-3) / 1e9,
             "sssp_trees_per_sec": trees / (ms_max * 1e-3),

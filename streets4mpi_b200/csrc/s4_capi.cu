@@ -51,17 +51,18 @@ static int fail(int code, const char *fmt, ...)
 // objects
 // ---------------------------------------------------------------------------
 struct Options {
-    double delta_factor = 2.0;
+    double delta_factor = 3.0;
     int block_threads = 0;          // 0 = from the graph (mean frontier width ~ V / hop depth)
     int ctas_per_sm = 0;            // 0 = as many CTAs as keep 1024 threads per SM
     int near_smem_entries = 0;      // 0 = 4 entries per thread
     int64_t queue_entries = 0;      // 0 = auto (from V)
     int64_t batch_roots = 0;        // 0 = auto (from pool_bytes)
-    double pool_bytes = 24.0e9;
+    double pool_bytes = 64.0e9;
     int root_mode = S4_ROOT_ORIGIN;
     int walk_tile = 8;
     int sssp_variant = 0;           // 0 = barrier per relaxation round, 1 = barrier-free ring
-    int preread = 1;                // read dist[head] before the atomic min
+    int preread = 2;                // 0: atomic straight away; 1: filtering read, then returning atomic;
+                                    // 2: filtering read decides the push, minimum sent as RED (no wait)
     int dist_l1 = 0;                // let L1 serve the filtering reads of dist[]
 };
 
@@ -72,6 +73,8 @@ struct s4_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t walk_stream = nullptr;     // second lane of the day loop (see s4_sim_step)
+    cudaEvent_t sssp_done[2] = {nullptr, nullptr}, walk_done[2] = {nullptr, nullptr};
     cudaDeviceProp prop;
     Options opt;
 };
@@ -179,6 +182,8 @@ static int grid_for(int64_t n, int block, const s4_ctx *ctx)
 extern "C" int s4_abi_version(void) { return S4_ABI_VERSION; }
 extern "C" const char *s4_last_error(void) { return g_err; }
 
+static void ctx_unref(s4_ctx *ctx);
+
 extern "C" int s4_ctx_create(int device, void *stream, s4_ctx **out)
 {
     CHECK_ARG(out, "s4_ctx_create: out is NULL");
@@ -202,6 +207,11 @@ extern "C" int s4_ctx_create(int device, void *stream, s4_ctx **out)
         if (se != cudaSuccess) { delete c; return fail(S4_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(se)); }
         c->own_stream = true;
     }
+    bool ok = cudaStreamCreateWithFlags(&c->walk_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; ++i)
+        ok = cudaEventCreateWithFlags(&c->sssp_done[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&c->walk_done[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { ctx_unref(c); return fail(S4_ERR_CUDA, "cannot create the walk stream / events"); }
     *out = c;
     return S4_OK;
 }
@@ -211,6 +221,11 @@ static void ctx_unref(s4_ctx *ctx)
     if (--ctx->refs > 0) return;
     cudaSetDevice(ctx->device);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->walk_stream) cudaStreamDestroy(ctx->walk_stream);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->sssp_done[i]) cudaEventDestroy(ctx->sssp_done[i]);
+        if (ctx->walk_done[i]) cudaEventDestroy(ctx->walk_done[i]);
+    }
     delete ctx;
 }
 
@@ -551,8 +566,8 @@ static int ensure_scratch(s4_graph *g, const SsspLaunch &L, int64_t slots_wanted
                                     : std::max<int64_t>(8192, std::max<int64_t>(65536, V / 4) * std::min(L.block, 256) / 256);
     q = std::min<int64_t>(q, std::max<int64_t>(V, 1024) * 2);
     if (L.grid > g->ws_ctas || (u32)q != g->near_gcap || !g->ws_v.p) {
-        CU(g->ws_v.alloc((size_t)L.grid * 4 * (size_t)q));
-        CU(g->ws_d.alloc((size_t)L.grid * 4 * (size_t)q));
+        CU(g->ws_v.alloc((size_t)2 * L.grid * 4 * (size_t)q));      // two lanes (concurrent launches)
+        CU(g->ws_d.alloc((size_t)2 * L.grid * 4 * (size_t)q));
         g->ws_ctas = L.grid;
         g->near_gcap = (u32)q;
         g->far_cap = (u32)q;
@@ -561,22 +576,24 @@ static int ensure_scratch(s4_graph *g, const SsspLaunch &L, int64_t slots_wanted
 }
 
 static int launch_sssp(s4_graph *g, const SsspLaunch &L, const Arc *ell, const Arc *arcs, const int32_t *d_roots,
-                       int n_roots, u32 *work_counter, const double *wsum, u64 *counters)
+                       int n_roots, u32 *work_counter, const double *wsum, u64 *counters, int64_t first_slot = 0,
+                       int lane = 0, cudaStream_t st = nullptr)
 {
+    if (!st) st = g->ctx->stream;
     SsspParams p;
     p.ell = ell;
     p.row_ptr = g->row_ptr.p;
     p.arcs = arcs;
-    p.dist_pool = g->pool.p;
     p.slot_stride = (size_t)((g->V + 3) & ~3);
+    p.dist_pool = g->pool.p + (size_t)first_slot * p.slot_stride;
     p.roots = d_roots;
     p.n_roots = n_roots;
     p.V = (u32)g->V;
     p.work_counter = work_counter;
     p.wsum = wsum;
     p.delta_scale = g->S > 0 ? g->ctx->opt.delta_factor / (double)g->S : 0.0;
-    p.ws_v = g->ws_v.p;
-    p.ws_d = g->ws_d.p;
+    p.ws_v = g->ws_v.p + (size_t)lane * g->ws_ctas * 4 * (size_t)g->near_gcap;
+    p.ws_d = g->ws_d.p + (size_t)lane * g->ws_ctas * 4 * (size_t)g->near_gcap;
     p.near_scap = L.scap;
     p.near_gcap = g->near_gcap;
     p.far_cap = g->far_cap;
@@ -584,7 +601,7 @@ static int launch_sssp(s4_graph *g, const SsspLaunch &L, const Arc *ell, const A
     p.dist_l1 = (u32)g->ctx->opt.dist_l1;
     p.counters = counters;
     const int grid = std::min(L.grid, std::max(1, n_roots));
-    L.fn<<<grid, L.block, L.smem, g->ctx->stream>>>(p);
+    L.fn<<<grid, L.block, L.smem, st>>>(p);
     CU(cudaGetLastError());
     return S4_OK;
 }
@@ -605,12 +622,11 @@ static int launch_pred(s4_graph *g, const Arc *arcs, const u64 *dist, u32 root, 
     return S4_OK;
 }
 
-static int launch_walk(s4_graph *g, const WalkParams &p)
+static int launch_walk(s4_graph *g, const WalkParams &p, cudaStream_t st)
 {
     const int tile = g->ctx->opt.walk_tile;
     const int block = 256;
     const int grid = grid_for((p.t1 - p.t0) * tile, block, g->ctx);
-    cudaStream_t st = g->ctx->stream;
     switch (tile) {
         case 4: walk_kernel<4><<<grid, block, 0, st>>>(p); break;
         case 8: walk_kernel<8><<<grid, block, 0, st>>>(p); break;
@@ -932,28 +948,41 @@ extern "C" int s4_sim_step(s4_sim *sim)
     if ((rc = run_weights(sim, 1))) return rc;
     if ((rc = ev_end(sim->ev_w, sim->used_w, st))) return rc;
 
-    // ---- K2 + K3 in batches of pool_slots roots (simulation.py:71-88)
+    // ---- K2 + K3 in batches (simulation.py:71-88).  With more than one batch the work runs in two
+    // independent lanes (own stream, own half of the distance pool, own frontier workspace): batch i goes
+    // to lane i & 1, where its SSSP launch is followed by its walk.  The persistent SSSP grid of one lane
+    // fills the SMs the other lane's launch frees while it drains its last trees, and the walk (a
+    // latency-bound pointer chase) hides under the other lane's SSSP.
     const int64_t D = sim->D;
-    const int64_t B = std::max<int64_t>(1, g->pool_slots);
+    const int64_t slots = std::max<int64_t>(1, g->pool_slots);
+    const bool split = D > slots && slots >= 2;
+    const int64_t B = split ? slots / 2 : slots;
     const int64_t n_batches = (D + B - 1) / B;
     if (n_batches > 0) {
         CU(g->work_counters.ensure((size_t)std::max<int64_t>(n_batches, 1024)));
         CU(cudaMemsetAsync(g->work_counters.p, 0, g->work_counters.n * sizeof(u32), st));
     }
+    if (split) {                                                   // lane 1 starts after K1 and the counter reset
+        CU(cudaEventRecord(ctx->sssp_done[0], st));
+        CU(cudaStreamWaitEvent(ctx->walk_stream, ctx->sssp_done[0], 0));
+    }
     for (int64_t bi = 0; bi < n_batches; ++bi) {
         const int64_t r0 = bi * B, r1 = std::min(D, r0 + B);
-        if ((rc = ev_begin(sim->ev_sssp, sim->used_sssp, st))) return rc;
+        const int lane = split ? (int)(bi & 1) : 0;
+        cudaStream_t ls = lane ? ctx->walk_stream : st;
+        const int64_t first_slot = lane * B;
+        if ((rc = ev_begin(sim->ev_sssp, sim->used_sssp, ls))) return rc;
         if ((rc = launch_sssp(g, L, sim->ell.p, sim->arcs.p, sim->roots.p + r0, (int)(r1 - r0), g->work_counters.p + bi,
-                              sim->wsum.p, sim->counters.p))) return rc;
-        if ((rc = ev_end(sim->ev_sssp, sim->used_sssp, st))) return rc;
+                              sim->wsum.p, sim->counters.p, first_slot, lane, ls))) return rc;
+        if ((rc = ev_end(sim->ev_sssp, sim->used_sssp, ls))) return rc;
         ++sim->acc.kernel_launches;
         ++sim->acc.sssp_launches;
         WalkParams wp;
         wp.row_ptr = g->row_ptr.p;
         wp.arcs = sim->arcs.p;
         wp.orig = g->orig.p;
-        wp.dist_pool = g->pool.p;
         wp.slot_stride = (size_t)((g->V + 3) & ~3);
+        wp.dist_pool = g->pool.p + (size_t)first_slot * wp.slot_stride;
         wp.roots = sim->roots.p;
         wp.trip_target = sim->trip_target.p;
         wp.trip_root = sim->trip_root.p;
@@ -964,10 +993,14 @@ extern "C" int s4_sim_step(s4_sim *sim)
         wp.volume = sim->volume;
         wp.load = sim->load.p;
         wp.counters = sim->counters.p;
-        if ((rc = ev_begin(sim->ev_walk, sim->used_walk, st))) return rc;
-        if ((rc = launch_walk(g, wp))) return rc;
-        if ((rc = ev_end(sim->ev_walk, sim->used_walk, st))) return rc;
+        if ((rc = ev_begin(sim->ev_walk, sim->used_walk, ls))) return rc;
+        if ((rc = launch_walk(g, wp, ls))) return rc;
+        if ((rc = ev_end(sim->ev_walk, sim->used_walk, ls))) return rc;
         ++sim->acc.kernel_launches;
+    }
+    if (split) {                                                   // the day ends when both lanes are done
+        CU(cudaEventRecord(ctx->walk_done[1], ctx->walk_stream));
+        CU(cudaStreamWaitEvent(st, ctx->walk_done[1], 0));
     }
     if ((rc = ev_end(sim->ev_step, sim->used_step, st))) return rc;
     sim->acc.days += 1;

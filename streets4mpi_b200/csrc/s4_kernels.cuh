@@ -252,6 +252,19 @@ __device__ __forceinline__ bool expand_entry(const Arc *__restrict__ ell, u64 *d
             else old[j] = ld_dist(dist + pv[j]);
         }
     }
+    if (preread == 2u) {
+        // fire-and-forget: the push is decided on the filtering read alone and the minimum is sent as a
+        // reduction (RED, no return value to wait for).  If another thread got a smaller value in first,
+        // the entry pushed here is simply superseded and dropped when it is popped (exact compare).
+#pragma unroll
+        for (int j = 0; j < kEllWidth; ++j) {
+            if (pd[j] < old[j]) {
+                atomicMin(dist + pv[j], pd[j]);
+                kind[j] = hi32(pd[j]) <= thr_hi ? 1u : 2u;
+            }
+        }
+        return true;
+    }
 #pragma unroll
     for (int j = 0; j < kEllWidth; ++j) {
         if (pd[j] < old[j]) {                                // padding slots have pd == +inf

@@ -280,6 +280,38 @@ def test_medium_day_vs_oracle(dev, phys, shape, n_trips):
     g.close()
 
 
+def test_small_pool_ping_pong_batches(dev, phys):
+    """A pool of 64 trees forces ~50 launches per day that alternate between the two pool halves while
+    the walks run on the second stream; the day must still equal the oracle's."""
+    from oracle import ctwin
+    from streets4mpi_b200 import engine, synth
+    arr = synth.grid_arrays(60, 70, seed=41)
+    V = len(arr["node_ids"])
+    rng = np.random.default_rng(9)
+    o = rng.integers(0, V, 2500).astype(np.int32)
+    gl = rng.integers(0, V, 2500).astype(np.int32)
+    old = dev.get_option("batch_roots")
+    try:
+        dev.set_option("batch_roots", 64)
+        dev.set_option("root_mode", 0)
+        g = engine.DeviceGraph(dev, V, arr["u"], arr["v"], arr["length"], arr["max_speed"])
+        sim = engine.DeviceSim(g, o, gl, 0.3, phys)
+        csr = ctwin.Csr(V, arr["u"], arr["v"])
+        prev = np.zeros(len(arr["u"]), dtype=np.uint32)
+        for _ in range(2):
+            sim.step()
+            want, cnt = ctwin.day(csr, ctwin.weights(arr["length"], arr["max_speed"], prev, 0.3), o, gl, nthreads=4)
+            assert np.array_equal(sim.get_load(), want)
+            sim.commit_total()
+            prev = want
+        c = sim.counters()
+        assert c["sssp_launches"] >= 2 * (sim.n_roots // 32) and c["hops"] > 0
+        sim.close()
+        g.close()
+    finally:
+        dev.set_option("batch_roots", old)
+
+
 def test_root_mode_invariance_unique_paths(dev, phys):
     """Origin-rooted (reference grouping) and goal-rooted trees give identical loads on continuous weights."""
     from streets4mpi_b200 import engine, synth
