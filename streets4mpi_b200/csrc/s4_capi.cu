@@ -378,6 +378,21 @@ extern "C" int s4_graph_upload(s4_ctx *ctx, int32_t V, int64_t S, const int32_t 
             ell_cs[(size_t)n * kEllWidth + k] = k < deg ? arc_cs[rb + k] : make_uint2((u32)n, 0xFFFFFFFFu);
         if (deg > (u32)kEllWidth) ell_cs[(size_t)n * kEllWidth].x |= kOvfBit;
     }
+    // slot of the reverse arc in the head's row (7 = not among its first kEllWidth arcs), packed above the street
+    if (S >= ((int64_t)1 << 29) || V >= (1 << 28)) return fail(S4_ERR_ARG, "graph too large for the packed frontier entries");
+    for (int32_t n = 0; n < V; ++n) {
+        for (u32 k = 0; k < (u32)kEllWidth; ++k) {
+            uint2 &slot = ell_cs[(size_t)n * kEllWidth + k];
+            if (slot.y == 0xFFFFFFFFu) continue;
+            const u32 h = slot.x & ~kOvfBit, street = slot.y & 0x1FFFFFFFu;
+            u32 rev = 7u;
+            for (u32 j = 0; j < (u32)kEllWidth; ++j) {
+                const uint2 &back = ell_cs[(size_t)h * kEllWidth + j];
+                if (back.y != 0xFFFFFFFFu && (back.x & ~kOvfBit) == (u32)n && (back.y & 0x1FFFFFFFu) == street) { rev = j; break; }
+            }
+            slot.y = street | (rev << 29);
+        }
+    }
     s4_graph *g = new (std::nothrow) s4_graph();
     if (!g) return fail(S4_ERR_OOM, "host allocation failed");
     g->ctx = ctx;

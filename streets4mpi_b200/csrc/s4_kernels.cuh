@@ -134,7 +134,8 @@ __global__ void weights_arc_kernel(int64_t A, const uint2 *__restrict__ arc_cs, 
     }
 }
 
-// per ELL slot: {head | overflow flag, street, w[street]}; padding slots carry street = ~0 and get w = +inf
+// per ELL slot: {head | overflow flag, slot of the reverse arc in the head's row, w[street]}.  The template
+// packs (reverse slot << 29 | street); padding slots carry ~0 and get w = +inf.
 __global__ void weights_ell_kernel(int64_t n_slots, const uint2 *__restrict__ ell_cs, const double *__restrict__ w_street,
                                    Arc *__restrict__ ell)
 {
@@ -142,8 +143,8 @@ __global__ void weights_ell_kernel(int64_t n_slots, const uint2 *__restrict__ el
         uint2 cs = ell_cs[e];
         Arc a;
         a.col = cs.x;
-        a.street = cs.y;
-        a.w = cs.y == 0xFFFFFFFFu ? __longlong_as_double((long long)kInfBits) : w_street[cs.y];
+        a.street = cs.y == 0xFFFFFFFFu ? 7u : cs.y >> 29;
+        a.w = cs.y == 0xFFFFFFFFu ? __longlong_as_double((long long)kInfBits) : w_street[cs.y & 0x1FFFFFFFu];
         ell[e] = a;
     }
 }
@@ -182,6 +183,8 @@ __global__ void driving_speed_kernel(int64_t n, const double *length, const int3
 // ---------------------------------------------------------------------------
 static constexpr int kEllWidth = 4;
 static constexpr u32 kOvfBit = 0x80000000u;
+static constexpr u32 kNodeMask = 0x0FFFFFFFu;   // frontier entry word: node | (skip slot << 28)
+static constexpr u32 kNoSkip = 7u << 28;
 
 struct SsspParams {
     const Arc *ell;         // V * kEllWidth
@@ -230,9 +233,12 @@ __device__ __forceinline__ u64 pick4(const u64 (&s)[4], u32 k)
 // them); then one 8-byte read per remaining neighbour; then atomicMin for the arcs that can win.
 // kind[j]: 0 nothing, 1 improved and inside the bucket, 2 improved and beyond it.  Returns false for a
 // superseded entry.  `ovf` reports a node with more than kEllWidth arcs.
-__device__ __forceinline__ bool expand_entry(const Arc *__restrict__ ell, u64 *dist, u32 u, u64 du, u32 thr_hi, u32 preread,
+__device__ __forceinline__ bool expand_entry(const Arc *__restrict__ ell, u64 *dist, u32 ent, u64 du, u32 thr_hi, u32 preread,
                                              u32 (&kind)[kEllWidth], u32 (&pv)[kEllWidth], u64 (&pd)[kEllWidth], bool &ovf)
 {
+    // entry word: node in bits 0..27, bits 28..30 = slot of the arc back to the node that pushed it (7 = none):
+    // relaxing that arc can never win (the pusher's distance is smaller), so it is neither read nor relaxed
+    const u32 u = ent & kNodeMask, skip = ent >> 28;
     Arc a[kEllWidth];
     u64 sec[4];
     const Arc *row = ell + (size_t)u * kEllWidth;
@@ -246,8 +252,9 @@ __device__ __forceinline__ bool expand_entry(const Arc *__restrict__ ell, u64 *d
     for (int j = 0; j < kEllWidth; ++j) {
         pv[j] = a[j].col & ~kOvfBit;
         pd[j] = (u64)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)du), a[j].w));
+        if ((u32)j == skip) pd[j] = kInfBits;
         old[j] = kInfBits;
-        if (preread) {
+        if (preread && pd[j] < kInfBits) {
             if ((pv[j] >> 2) == (u >> 2)) old[j] = pick4(sec, pv[j] & 3u);
             else old[j] = ld_dist(dist + pv[j]);
         }
@@ -261,6 +268,7 @@ __device__ __forceinline__ bool expand_entry(const Arc *__restrict__ ell, u64 *d
             if (pd[j] < old[j]) {
                 atomicMin(dist + pv[j], pd[j]);
                 kind[j] = hi32(pd[j]) <= thr_hi ? 1u : 2u;
+                pv[j] |= a[j].street << 28;
             }
         }
         return true;
@@ -269,7 +277,7 @@ __device__ __forceinline__ bool expand_entry(const Arc *__restrict__ ell, u64 *d
     for (int j = 0; j < kEllWidth; ++j) {
         if (pd[j] < old[j]) {                                // padding slots have pd == +inf
             const u64 o2 = atomicMin(dist + pv[j], pd[j]);
-            if (pd[j] < o2) kind[j] = hi32(pd[j]) <= thr_hi ? 1u : 2u;
+            if (pd[j] < o2) { kind[j] = hi32(pd[j]) <= thr_hi ? 1u : 2u; pv[j] |= a[j].street << 28; }
         }
     }
     return true;
@@ -382,7 +390,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024
             s_far_cnt[0] = 0u; s_far_cnt[1] = 0u;
             s_far_min[0] = 0xFFFFFFFFu; s_far_min[1] = 0xFFFFFFFFu;
             s_overflow = 0u;
-            sv0[0] = root; sd0[0] = 0ull;
+            sv0[0] = root | kNoSkip; sd0[0] = 0ull;
         }
         __syncthreads();
         if (tid == 0) dist[root] = 0ull;                   // after the fill
@@ -426,13 +434,13 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024
                     // nodes with more than kEllWidth arcs: the rest of the CSR row, one arc per step
                     if (__any_sync(0xffffffffu, ovf)) {
                         u32 e = 0, re = 0;
-                        if (ovf) { e = __ldg(p.row_ptr + u) + kEllWidth; re = __ldg(p.row_ptr + u + 1); }
+                        if (ovf) { e = __ldg(p.row_ptr + (u & kNodeMask)) + kEllWidth; re = __ldg(p.row_ptr + (u & kNodeMask) + 1); }
                         while (__any_sync(0xffffffffu, e < re)) {
                             u32 k1[1] = {0u}, v1[1] = {0u};
                             u64 d1[1] = {0ull};
                             if (e < re) {
                                 const Arc x = ld_arc(p.arcs + e);
-                                v1[0] = x.col;
+                                v1[0] = x.col | kNoSkip;
                                 d1[0] = (u64)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)du), x.w));
                                 if (d1[0] < ld_dist(dist + x.col)) {
                                     const u64 o2 = atomicMin(dist + x.col, d1[0]);
@@ -665,7 +673,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024
             s_far_cnt[0] = 0u; s_far_cnt[1] = 0u;
             s_far_min[0] = 0xFFFFFFFFu; s_far_min[1] = 0xFFFFFFFFu;
             s_overflow = 0u;
-            rd[0] = 0ull; rv[0] = root;
+            rd[0] = 0ull; rv[0] = root | kNoSkip;
         }
         __syncthreads();
         if (tid == 0) dist[root] = 0ull;
@@ -716,13 +724,13 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024
                 warp_push_async<kEllWidth>(kind, pv, pd, lane, R, fv, fd, &s_far_cnt[f], &s_far_min[f], fcap, &s_overflow, c_push);
                 if (__any_sync(0xffffffffu, ovf)) {
                     u32 e = 0, re = 0;
-                    if (ovf) { e = __ldg(p.row_ptr + u) + kEllWidth; re = __ldg(p.row_ptr + u + 1); }
+                    if (ovf) { e = __ldg(p.row_ptr + (u & kNodeMask)) + kEllWidth; re = __ldg(p.row_ptr + (u & kNodeMask) + 1); }
                     while (__any_sync(0xffffffffu, e < re)) {
                         u32 k1[1] = {0u}, v1[1] = {0u};
                         u64 d1[1] = {0ull};
                         if (e < re) {
                             const Arc x = ld_arc(p.arcs + e);
-                            v1[0] = x.col;
+                            v1[0] = x.col | kNoSkip;
                             d1[0] = (u64)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)du), x.w));
                             if (d1[0] < ld_dist(dist + x.col)) {
                                 const u64 o2 = atomicMin(dist + x.col, d1[0]);
