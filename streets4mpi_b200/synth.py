@@ -106,3 +106,57 @@ def parse_spec(spec):
     if parts[1] == "planar":
         return planar_arrays(int(parts[2]), seed)
     raise ValueError("unknown synthetic network kind %r" % (parts[1],))
+
+
+def write_osm_xml(path, rows=24, cols=30, seed=7, lat0=53.585, lon0=9.915, spacing_m=120.0):
+    """A small 'Hamburg-Stellingen-like' OSM XML file (the reference's osm/test.osm is a missing blob):
+    a jittered street grid with a road-class mix, a few explicit maxspeed tags (digits, mph, none), footways,
+    and landuse polygons / one landuse relation that reuse street nodes, so that the residential, commercial
+    and industrial node sets are connected to the network."""
+    rng = np.random.default_rng(seed)
+    dlat = spacing_m / 111320.0
+    dlon = spacing_m / (111320.0 * np.cos(np.radians(lat0)))
+    nid = lambda r, c: 100000 + r * cols + c
+    out = ['<?xml version="1.0" encoding="UTF-8"?>', '<osm version="0.6" generator="streets4mpi_b200.synth">']
+    for r in range(rows):
+        for c in range(cols):
+            la = lat0 + (r + rng.uniform(-0.25, 0.25)) * dlat
+            lo = lon0 + (c + rng.uniform(-0.25, 0.25)) * dlon
+            out.append('<node id="%d" lat="%.7f" lon="%.7f"/>' % (nid(r, c), la, lo))
+    wid = [500000]
+
+    def way(refs, tags):
+        wid[0] += 1
+        out.append('<way id="%d">' % wid[0])
+        out.extend('<nd ref="%d"/>' % x for x in refs)
+        out.extend('<tag k="%s" v="%s"/>' % kv for kv in tags.items())
+        out.append("</way>")
+        return wid[0]
+
+    classes = ["residential"] * 6 + ["tertiary", "tertiary", "secondary", "unclassified", "service", "footway"]
+    for r in range(rows):
+        tags = {"highway": "primary" if r == rows // 2 else str(rng.choice(classes))}
+        if r % 7 == 3:
+            tags["maxspeed"] = str(rng.choice(["30", "50", "30 mph", "none"]))
+        way([nid(r, c) for c in range(cols)], tags)
+    for c in range(cols):
+        tags = {"highway": "motorway" if c == cols // 3 else str(rng.choice(classes))}
+        if c % 9 == 4:
+            tags["maxspeed"] = str(rng.choice(["20", "60", "70"]))
+        way([nid(r, c) for r in range(rows)], tags)
+
+    def block(r0, c0, h, w_):
+        ring = [nid(r0, c) for c in range(c0, c0 + w_)] + [nid(r, c0 + w_ - 1) for r in range(r0 + 1, r0 + h)]
+        ring += [nid(r0 + h - 1, c) for c in range(c0 + w_ - 2, c0 - 1, -1)] + [nid(r, c0) for r in range(r0 + h - 2, r0, -1)]
+        return ring + [ring[0]]
+    way(block(1, 1, rows // 3, cols // 3), {"landuse": "residential"})
+    way(block(rows // 2 + 1, 2, rows // 3, cols // 4), {"landuse": "residential"})
+    w_ind = way(block(2, cols // 2 + 2, rows // 4, cols // 4), {"landuse": "industrial"})
+    w_com = way(block(rows // 2, cols // 2, rows // 4, cols // 3), {"landuse": "commercial"})
+    w_com2 = way(block(rows - 6, cols - 8, 4, 5), {})
+    out.append('<relation id="900001"><member type="way" ref="%d" role="outer"/><tag k="landuse" v="commercial"/>'
+               '<tag k="type" v="multipolygon"/></relation>' % w_com2)
+    out.append("</osm>")
+    with open(path, "w") as f:
+        f.write("\n".join(out))
+    return {"rows": rows, "cols": cols, "industrial_way": w_ind, "commercial_way": w_com}

@@ -135,3 +135,57 @@ def test_streets4mpi_driver_end_to_end(tmp_path):
         os.chdir(cwd)
         settings.clear()
         settings.update(old)
+
+
+@pytest.mark.parametrize("residents,every", [(100, 10), (3000, 4)])
+def test_streets4mpi_on_osm_file_matches_port(tmp_path, residents, every):
+    """BASELINE configs[0]/[1] stand-in: the zero-argument driver on an OSM XML file (the reference's
+    osm/test.osm is a missing blob; synth.write_osm_xml generates a Stellingen-like one) with settings.py
+    defaults, against the oracle's line-by-line port fed with the same trips and jam tolerance."""
+    import random
+    from oracle import port
+    from streets4mpi_b200 import persistence, synth
+    from streets4mpi_b200.osmdata import GraphBuilder
+    from streets4mpi_b200.settings import device_settings, settings
+    from streets4mpi_b200.streets4mpi import Streets4MPI
+    osm = str(tmp_path / "test.osm")
+    synth.write_osm_xml(osm, rows=14, cols=17, seed=5)
+    old, old_dev = dict(settings), dict(device_settings)
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        settings.update({"osm_file": osm, "logging": None, "number_of_residents": residents,
+                         "steps_between_street_construction": every})
+        device_settings["root_mode"] = 0
+        app = Streets4MPI()
+        days = settings["max_simulation_steps"]
+        got = [list(persistence.persist_read("traffic_load_%d.s4mpi" % (d + 1), is_array=True)) for d in range(days)]
+        # the same run through the oracle port
+        b = GraphBuilder(osm)
+        src = b.build_street_network()
+        b.find_node_categories()
+        def make():
+            net = port.Network(sssp="canonical")
+            for n in src.get_nodes():
+                net.add_node(n, *src.node_coordinates(n))
+            for i in range(src.street_index):
+                u, v = src.get_street_by_index(i)
+                at = src._graph.edge_attributes((u, v))
+                net.add_street((u, v), at[1], at[2])
+            return net
+        random.seed(settings["random_seed"])
+        goals = b.connected_commercial_nodes | b.connected_industrial_nodes
+        trips = port.generate_trips(residents, src.get_nodes(), goals)
+        jam = random.random()
+        assert jam == app.simulation.jam_tolerance
+        totals, net0 = port.run_days(make, [trips], [jam], days, every)
+        for d in range(days):
+            assert got[d] == list(totals[d]), "day %d" % (d + 1)
+        assert sum(got[-1]) > 0
+        seen_gpu = dict((idx, ms) for (_s, idx, _l, ms) in app.simulation.street_network)
+        seen_port = dict((idx, ms) for (_s, idx, _l, ms) in net0)
+        assert seen_gpu == seen_port
+    finally:
+        os.chdir(cwd)
+        settings.clear(); settings.update(old)
+        device_settings.clear(); device_settings.update(old_dev)

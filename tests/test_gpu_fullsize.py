@@ -1,0 +1,83 @@
+"""BASELINE-sized checks (cfg3: 1024x1024 grid, V=1,048,576, A=4,190,208).  The oracle cannot route a whole
+day at this size in test time, so the day is checked through size-independent properties and a sample of
+trees / trips is compared with the oracle's C twin exactly."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cfg3():
+    from streets4mpi_b200 import engine, synth
+    from streets4mpi_b200.settings import settings
+    dev = engine.default_device()
+    arr = synth.grid_arrays(1024, 1024, seed=1)
+    net = synth.network_from(arr)
+    flat = net.flat()
+    g = engine.DeviceGraph(dev, flat.V, flat.u, flat.v, flat.length, flat.max_speed, node_rank=flat.locality_rank())
+    cats = synth.node_categories(arr["node_ids"], seed=1, goal_fraction=0.02)
+    return dict(dev=dev, arr=arr, flat=flat, g=g, cats=cats, phys=engine.make_physics(settings))
+
+
+def test_fullsize_trees_bit_exact(cfg3):
+    """Three full trees on the 1M-node graph: distances bit-equal, predecessors equal."""
+    from oracle import ctwin
+    arr, g = cfg3["arr"], cfg3["g"]
+    rng = np.random.default_rng(11)
+    w = rng.uniform(0.1, 13.0, size=len(arr["u"]))
+    csr = ctwin.Csr(len(arr["node_ids"]), arr["u"], arr["v"])
+    for src in (0, 524800, 1048575):
+        dist, pred = g.sssp(w, src)
+        d0, p0, tied = ctwin.sssp(csr, w, src)
+        assert np.array_equal(dist.view(np.uint64), d0.view(np.uint64))
+        assert np.array_equal(pred, p0)
+        # symmetry of the undirected graph: d(src, t) == d(t, src) up to the rounding of the reversed sum
+        t = int(rng.integers(0, len(dist)))
+        back, _ = g.sssp(w, t, want_pred=False)
+        assert abs(back[src] - dist[t]) <= 1e-6 * dist[t]          # the north_star's cost tolerance
+
+
+def test_fullsize_day_properties(cfg3):
+    """100k trips on cfg3 (5 % of the day's goals -> ~1000 trees): conservation (sum of loads == hops x
+    volume), no stuck / unreachable trips, repeatability, root-mode invariance, and a 60-trip sample routed
+    by the oracle equals the GPU's load for exactly those trips."""
+    from oracle import ctwin
+    from streets4mpi_b200 import engine, synth
+    dev, arr, g, cats, phys = cfg3["dev"], cfg3["arr"], cfg3["g"], cfg3["cats"], cfg3["phys"]
+    goals = cats["goals"][:1000]
+    o, gl = synth.trip_arrays(100000, arr["node_ids"], goals, seed=3756917)
+    o, gl = o.astype(np.int32), gl.astype(np.int32)
+    loads = {}
+    for mode in (1, 1, 0):                                   # goal-rooted twice, then a sample origin-rooted
+        dev.set_option("root_mode", mode)
+        if mode == 0:
+            oo, gg = o[:1500], gl[:1500]
+        else:
+            oo, gg = o, gl
+        sim = engine.DeviceSim(g, oo, gg, 0.4, phys)
+        sim.step()
+        load = sim.get_load()
+        c = sim.counters()
+        assert c["trips_routed"] == len(oo) and c["trips_unreachable"] == 0 and c["trips_stuck"] == 0
+        assert c["fallback_sweeps"] == 0
+        assert int(load.astype(np.int64).sum()) == c["hops"] * phys.trip_volume
+        loads.setdefault(mode, []).append(load)
+        if mode == 0:
+            dev.set_option("root_mode", 1)
+            sim2 = engine.DeviceSim(g, oo, gg, 0.4, phys)
+            sim2.step()
+            assert np.array_equal(sim2.get_load(), load)      # origin- vs goal-rooted, unique paths
+            sim2.close()
+        sim.close()
+    dev.set_option("root_mode", 0)
+    assert np.array_equal(loads[1][0], loads[1][1])           # repeatable to the bit
+    # sample against the oracle
+    sample = slice(0, 60)
+    csr = ctwin.Csr(len(arr["node_ids"]), arr["u"], arr["v"])
+    w = ctwin.weights(arr["length"], arr["max_speed"], np.zeros(len(arr["u"]), dtype=np.uint32), 0.4)
+    want, cnt = ctwin.day(csr, w, o[sample], gl[sample], nthreads=8)
+    sim = engine.DeviceSim(g, o[sample], gl[sample], 0.4, phys)
+    sim.step()
+    assert cnt["tied_trips"] == 0 and np.array_equal(sim.get_load(), want)
+    sim.close()

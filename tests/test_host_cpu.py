@@ -192,3 +192,35 @@ def test_rank_seeding_known_answers():
     random.seed(distributed.rank_seed(3756917, 7))
     assert random.random() == 0.0975399640380532
     assert distributed.residents_of_rank(100, 8) == 12 and distributed.residents_of_rank(100000, 3) == 33333
+
+
+def test_osm_ingest_rules(tmp_path):
+    """osmdata.GraphBuilder on a generated OSM XML file: the reference's construction rules."""
+    from streets4mpi_b200 import synth
+    from streets4mpi_b200.osmdata import GraphBuilder, haversine_m, speed_limit
+    path = str(tmp_path / "test.osm")
+    meta = synth.write_osm_xml(path, rows=10, cols=12, seed=3)
+    b = GraphBuilder(path)
+    net = b.build_street_network()
+    assert len(net.get_nodes()) == 120 and net.street_index == 10 * 11 + 12 * 9
+    assert net.bounds is not None and net.bounds[0][0] < net.bounds[0][1]
+    # first way wins, every consecutive ref pair is a street, lengths are haversine metres
+    (st, idx, length, ms) = next(iter(net))
+    assert 60.0 < length < 200.0 and ms >= 1
+    la1, lo1 = b.coords[st[0]]
+    la2, lo2 = b.coords[st[1]]
+    assert length == haversine_m(la1, lo1, la2, lo2)
+    assert abs(haversine_m(53.5, 9.9, 53.6, 9.9) - 6367000 * np.radians(0.1)) < 1e-6
+    # speed-limit rules (osmdata.py:119-129)
+    assert speed_limit({"highway": "motorway"}) == 140 and speed_limit({"highway": "footway"}) == 1
+    assert speed_limit({"highway": "bogus"}) == 50 and speed_limit({"highway": "residential", "maxspeed": "70"}) == 70
+    assert speed_limit({"highway": "primary", "maxspeed": "30 mph"}) == 30          # no unit conversion
+    assert speed_limit({"highway": "primary", "maxspeed": "none"}) == 140
+    assert speed_limit({"highway": "primary", "maxspeed": "walk"}) == 100
+    b.find_node_categories()
+    assert b.connected_residential_nodes and b.connected_industrial_nodes and b.connected_commercial_nodes
+    assert b.connected_industrial_nodes == set(b.all_osm_ways[meta["industrial_way"]][2])
+    assert b.connected_commercial_nodes > set(b.all_osm_ways[meta["commercial_way"]][2])    # + the relation's way
+    assert b.get_all_child_nodes(123456789) == set()
+    flat = net.flat()
+    assert flat.locality_rank() is not None and sorted(flat.locality_rank().tolist()) == list(range(120))
