@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libs4mpi.so")
+LIB_PATH = os.environ.get("S4MPI_LIB") or os.path.join(_HERE, "libs4mpi.so")    # override: A/B kernel builds
 
 ROOT_ORIGIN, ROOT_GOAL, ROOT_AUTO = 0, 1, 2
 

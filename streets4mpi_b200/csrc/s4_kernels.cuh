@@ -143,7 +143,7 @@ __global__ void weights_ell_kernel(int64_t n_slots, const uint2 *__restrict__ el
         uint2 cs = ell_cs[e];
         Arc a;
         a.col = cs.x;
-        a.street = cs.y == 0xFFFFFFFFu ? 7u : cs.y >> 29;
+        a.street = (cs.x & 0x0FFFFFFFu) | ((cs.y == 0xFFFFFFFFu ? 7u : cs.y >> 29) << 28);   // entry word of the head
         a.w = cs.y == 0xFFFFFFFFu ? __longlong_as_double((long long)kInfBits) : w_street[cs.y & 0x1FFFFFFFu];
         ell[e] = a;
     }
@@ -268,7 +268,7 @@ __device__ __forceinline__ bool expand_entry(const Arc *__restrict__ ell, u64 *d
             if (pd[j] < old[j]) {
                 atomicMin(dist + pv[j], pd[j]);
                 kind[j] = hi32(pd[j]) <= thr_hi ? 1u : 2u;
-                pv[j] |= a[j].street << 28;
+                pv[j] = a[j].street;
             }
         }
         return true;
@@ -277,7 +277,7 @@ __device__ __forceinline__ bool expand_entry(const Arc *__restrict__ ell, u64 *d
     for (int j = 0; j < kEllWidth; ++j) {
         if (pd[j] < old[j]) {                                // padding slots have pd == +inf
             const u64 o2 = atomicMin(dist + pv[j], pd[j]);
-            if (pd[j] < o2) { kind[j] = hi32(pd[j]) <= thr_hi ? 1u : 2u; pv[j] |= a[j].street << 28; }
+            if (pd[j] < o2) { kind[j] = hi32(pd[j]) <= thr_hi ? 1u : 2u; pv[j] = a[j].street; }
         }
     }
     return true;
@@ -305,7 +305,7 @@ __device__ __forceinline__ void warp_push(const u32 (&kind)[N], const u32 (&pv)[
     u32 packed = 0, mymin = 0xFFFFFFFFu;
 #pragma unroll
     for (int j = 0; j < N; ++j) {
-        packed += (kind[j] == 1u ? 1u : 0u) + (kind[j] == 2u ? 0x10000u : 0u);
+        packed += (kind[j] & 1u) | ((kind[j] & 2u) << 15);     // near count low half, far count high half
         if (kind[j] == 2u) mymin = min(mymin, hi32(pd[j]));
     }
     u32 incl = packed;
@@ -328,12 +328,13 @@ __device__ __forceinline__ void warp_push(const u32 (&kind)[N], const u32 (&pv)[
     u32 on = base_n + (excl & 0xFFFFu), of = base_f + (excl >> 16);
 #pragma unroll
     for (int j = 0; j < N; ++j) {
-        if (kind[j] == 1u) { q_store(nq, scap, gcap, on++, pv[j], pd[j], overflow); ++c_push; }
+        if (kind[j] == 1u) q_store(nq, scap, gcap, on++, pv[j], pd[j], overflow);
         else if (kind[j] == 2u) {
             if (of < fcap) { far_v[of] = pv[j]; far_d[of] = pd[j]; } else *overflow = 1u;
-            ++of; ++c_push;
+            ++of;
         }
     }
+    c_push += (packed & 0xFFFFu) + (packed >> 16);
 }
 
 template <int BLOCK>

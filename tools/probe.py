@@ -74,6 +74,7 @@ for cfg in configs:
                relax_x=round(c["arcs_relaxed"] / max(1, c["arcs_algorithmic"]), 2),
                pops_x=round(c["nodes_popped"] / max(1, c["nodes_algorithmic"]), 2),
                stale_x=round(c["stale_pops"] / max(1, c["nodes_algorithmic"]), 2),
+               push_x=round(c["queue_pushes"] / max(1, c["nodes_algorithmic"]), 2),
                rounds=c["relax_rounds"] // sim.n_roots, adv=c["bucket_advances"] // sim.n_roots,
                fb=c["fallback_sweeps"], hops=c["hops"])
     print(json.dumps(out), flush=True)
