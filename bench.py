@@ -33,10 +33,13 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 RANDOM_SEED = 3756917          # settings.py:29
+TRIPS_OVERRIDE = 0
 WORKLOADS = {
-    # name: (rows, cols, trips per day in total)
+    # name: (rows, cols, trips per day in total); rows == 0: random planar road graph with `cols` nodes
     "cfg3_grid1024": (1024, 1024, 1_000_000),
     "grid256": (256, 256, 100_000),           # quick functional run
+    "cfg4_planar5m": (0, 5_000_000, 10_000_000),   # BASELINE.json configs[3] (adaptation every 5 days)
+    "planar200k": (0, 200_000, 200_000),
 }
 
 
@@ -50,7 +53,9 @@ def log(*a):
 def make_workload(name, world):
     from streets4mpi_b200 import synth
     rows, cols, trips_total = WORKLOADS[name]
-    arrays = synth.grid_arrays(rows, cols, seed=1)
+    if TRIPS_OVERRIDE:
+        trips_total = TRIPS_OVERRIDE
+    arrays = synth.grid_arrays(rows, cols, seed=1) if rows else synth.planar_arrays(cols, seed=1)
     cats = synth.node_categories(arrays["node_ids"], seed=1, goal_fraction=0.02)
     per_rank = trips_total // world                       # streets4mpi.py:69
     return arrays, cats, per_rank
@@ -241,6 +246,10 @@ def reference_arm(args):
 
 def workload_text(name):
     rows, cols, trips = WORKLOADS[name]
+    trips = TRIPS_OVERRIDE or trips
+    if not rows:
+        return ("synthetic random planar road graph (thinned Delaunay, V=%d, S=%d, A=%d), %d trips/day, goals = 2%% node "
+                "sample, BASELINE.json configs[3] shape" % (cols, int(1.2 * cols), int(2.4 * cols), trips))
     return ("synthetic %dx%d grid street network (V=%d, S=%d, A=%d), %d trips/day, goals = 2%% node sample, "
             "BASELINE.json configs[2]" % (rows, cols, rows * cols, 2 * rows * cols - rows - cols,
                                           2 * (2 * rows * cols - rows - cols), trips))
@@ -299,10 +308,15 @@ def gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize(local)
 
+    day_no = [0]
+
     def day_resident():
         with torch.cuda.stream(stream):
+            if args.construction_every and day_no[0] > 0 and day_no[0] % args.construction_every == 0:
+                sim.road_construction()                     # streets4mpi.py:86-88
             sim.step()
             sim.exchange()
+            day_no[0] += 1
 
     # ---- resident-in-HBM timing: W warm-up days, then exactly K days between two events
     for _ in range(args.warmup):
@@ -317,8 +331,7 @@ def gpu_arm(args):
     with torch.cuda.stream(stream):
         e0.record(stream)
         for _ in range(args.steps):
-            sim.step()
-            sim.exchange()
+            day_resident()
         e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
@@ -380,7 +393,8 @@ def gpu_arm(args):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload + ": " + workload_text(args.workload),
                        "root_mode": "%s (trees per day and GPU: %d)" % (mode, sim._sim.n_roots),
-                       "virtual_ranks": world, "l2": "inputs larger than L2 (per-tree distance arrays, 8 B x V x trees in flight >> 126 MB)",
+                       "virtual_ranks": world, "construction_every": args.construction_every,
+                       "l2": "inputs larger than L2 (per-tree distance arrays, 8 B x V x trees in flight >> 126 MB)",
                        "options": args.options or "defaults"},
             "gteps": arcs_alg / (ms_max * 1e-3) / 1e9,
             "sssp_trees_per_sec": trees / (ms_max * 1e-3),
@@ -420,7 +434,11 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-trees-per-core", type=int, default=1)
+    ap.add_argument("--trips", type=int, default=0, help="override the workload's trips per day")
+    ap.add_argument("--construction-every", type=int, default=0, help="road adaptation every N days (0 = never)")
     args = ap.parse_args()
+    global TRIPS_OVERRIDE
+    TRIPS_OVERRIDE = args.trips
     if args.impl == "reference":
         if int(os.environ.get("RANK", "0")) != 0:
             return

@@ -534,7 +534,18 @@ struct SsspLaunch {
 static int plan_sssp(s4_graph *g, SsspLaunch *L)
 {
     const Options &o = g->ctx->opt;
-    const int block = o.block_threads ? o.block_threads : g->auto_block;
+    int block = o.block_threads ? o.block_threads : g->auto_block;
+    if (!o.block_threads) {
+        // narrow CTAs only pay off when that many trees fit in flight: each needs a distance slot (8 B x V)
+        size_t free_b = 0, total_b = 0;
+        CU(cudaMemGetInfo(&free_b, &total_b));
+        if (g->pool.p) free_b += g->pool.n * sizeof(u64);
+        const double per_slot = 8.0 * (double)g->V;
+        const int64_t slots = o.batch_roots > 0 ? o.batch_roots
+                                                : (int64_t)(std::min(o.pool_bytes, 0.6 * (double)free_b) / per_slot);
+        const int64_t per_lane = std::max<int64_t>(1, slots / 2);
+        while (block < 1024 && (int64_t)g->ctx->prop.multiProcessorCount * std::min(32, 1024 / block) > per_lane) block *= 2;
+    }
     const int near_entries = o.near_smem_entries ? o.near_smem_entries : std::max(128, 4 * block);
     const int ctas = o.ctas_per_sm ? o.ctas_per_sm : std::min(32, std::max(1, 1024 / block));
     L->fn = pick_sssp(block, o.sssp_variant);

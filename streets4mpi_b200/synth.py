@@ -54,8 +54,9 @@ def planar_arrays(n_nodes, seed=1, mean_degree=2.4, extent=None):
     e = np.unique(e, axis=0)
     d = np.hypot(*(pts[e[:, 0]] - pts[e[:, 1]]).T)
     mst = minimum_spanning_tree(coo_matrix((d, (e[:, 0], e[:, 1])), shape=(n_nodes, n_nodes))).tocoo()
-    in_tree = set(zip(mst.row.tolist(), mst.col.tolist()))
-    tree_mask = np.fromiter(((a, b) in in_tree or (b, a) in in_tree for a, b in e.tolist()), dtype=bool, count=len(e))
+    key = e[:, 0].astype(np.int64) * n_nodes + e[:, 1]
+    lo, hi = np.minimum(mst.row, mst.col).astype(np.int64), np.maximum(mst.row, mst.col).astype(np.int64)
+    tree_mask = np.isin(key, lo * n_nodes + hi)
     want = int(mean_degree * n_nodes / 2)
     extra = max(0, want - int(tree_mask.sum()))
     rest = np.nonzero(~tree_mask)[0]
