@@ -96,7 +96,7 @@ int s4_ctx_destroy(s4_ctx *ctx);
 int s4_ctx_sync(s4_ctx *ctx);
 /* Tunables (all have defaults): "delta_factor" (bucket width in mean arc
  * weights), "block_threads" (32|64|128|256|512|1024), "ctas_per_sm", "near_smem_entries", "queue_entries", "batch_roots",
- * "pool_bytes", "root_mode" (S4_ROOT_*), "walk_tile" (4|8|16|32),
+ * "pool_bytes", "root_mode" (S4_ROOT_*), "walk_tile" (0 = auto|4|8|16|32),
  * "sssp_variant" (0 = barrier per relaxation round, 1 = barrier-free ring),
  * "preread" (0 = atomicMin straight away, 1 = filtering read then returning
  * atomicMin, 2 = filtering read decides the push and the minimum goes out as a

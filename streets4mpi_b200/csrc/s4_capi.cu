@@ -59,7 +59,7 @@ struct Options {
     int64_t batch_roots = 0;        // 0 = auto (from pool_bytes)
     double pool_bytes = 64.0e9;
     int root_mode = S4_ROOT_ORIGIN;
-    int walk_tile = 8;
+    int walk_tile = 0;              // lanes per walking trip; 0 = from the graph's degrees
     int sssp_variant = 0;           // 0 = barrier per relaxation round, 1 = barrier-free ring
     int preread = 2;                // 0: atomic straight away; 1: filtering read, then returning atomic;
                                     // 2: filtering read decides the push, minimum sent as RED (no wait)
@@ -120,6 +120,7 @@ struct s4_graph {
     std::vector<int32_t> comp_of;
     std::vector<int64_t> comp_arcs, comp_nodes;
     int auto_block = 256;      // CTA width chosen from the graph's shape (see graph upload)
+    int auto_walk_tile = 8;    // lanes per walking trip: 4 when (almost) every node has at most 4 arcs
     // scratch shared by every simulation on this graph (sized lazily)
     DevBuf<u64> pool;          // slots * V
     int64_t pool_slots = 0;
@@ -280,7 +281,7 @@ extern "C" int s4_ctx_set_option(s4_ctx *ctx, const char *key, double value)
               t.ctas_per_sm >= 0 && t.ctas_per_sm <= 32 &&
               (t.near_smem_entries == 0 || (t.near_smem_entries >= 32 && t.near_smem_entries <= 9000)) && t.queue_entries >= 0 &&
               t.batch_roots >= 0 && t.pool_bytes >= 0.0 && t.root_mode >= 0 && t.root_mode <= 2 &&
-              (t.walk_tile == 4 || t.walk_tile == 8 || t.walk_tile == 16 || t.walk_tile == 32) &&
+              (t.walk_tile == 0 || t.walk_tile == 4 || t.walk_tile == 8 || t.walk_tile == 16 || t.walk_tile == 32) &&
               (t.sssp_variant == 0 || t.sssp_variant == 1);
     if (!ok) return fail(S4_ERR_ARG, "option '%s': value %g out of range", key, value);
     ctx->opt = trial;
@@ -456,6 +457,9 @@ extern "C" int s4_graph_upload(s4_ctx *ctx, int32_t V, int64_t S, const int32_t 
         int blk = 32;
         while (blk < 256 && (double)blk * 2.0 <= width) blk *= 2;
         g->auto_block = blk;
+        int64_t wide = 0;
+        for (int32_t i = 0; i < V; ++i) wide += (row_ptr[(size_t)i + 1] - row_ptr[(size_t)i]) > 4u;
+        g->auto_walk_tile = wide * 100 < (int64_t)V ? 4 : 8;
     }
     auto bail = [&](cudaError_t e, const char *what) {
         delete g;
@@ -634,7 +638,7 @@ static int launch_sssp(s4_graph *g, const SsspLaunch &L, const Arc *ell, const A
 
 static int launch_pred(s4_graph *g, const Arc *arcs, const u64 *dist, u32 root, int32_t *pred, double *dist_out)
 {
-    const int tile = g->ctx->opt.walk_tile;
+    const int tile = g->ctx->opt.walk_tile ? g->ctx->opt.walk_tile : g->auto_walk_tile;
     const int block = 256;
     const int grid = grid_for((int64_t)g->V * tile, block, g->ctx);
     cudaStream_t st = g->ctx->stream;
@@ -650,7 +654,7 @@ static int launch_pred(s4_graph *g, const Arc *arcs, const u64 *dist, u32 root, 
 
 static int launch_walk(s4_graph *g, const WalkParams &p, cudaStream_t st)
 {
-    const int tile = g->ctx->opt.walk_tile;
+    const int tile = g->ctx->opt.walk_tile ? g->ctx->opt.walk_tile : g->auto_walk_tile;
     const int block = 256;
     const int grid = grid_for((p.t1 - p.t0) * tile, block, g->ctx);
     switch (tile) {

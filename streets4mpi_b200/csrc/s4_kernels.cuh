@@ -824,12 +824,39 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024
 // Returns the packed key (id(u) << 32 | street), ~0 if there is none; *col_out is
 // the device number of the winner and *du_out its distance (valid on every lane).
 // ---------------------------------------------------------------------------
-template <int TILE>
+template <int TILE, bool WANT_ID>
 __device__ __forceinline__ u64 canonical_pred(const cg::thread_block_tile<TILE> &tile, const u32 *__restrict__ row_ptr,
                                               const Arc *__restrict__ arcs, const u32 *__restrict__ orig, const u64 *dist,
                                               u32 cur, u64 dv, u32 *col_out, u64 *du_out)
 {
     const u32 rb = __ldg(row_ptr + cur), re = __ldg(row_ptr + cur + 1);
+    // pass 1: which arcs reproduce dist[cur] exactly?  Almost always exactly one (unique shortest path):
+    // then neither the ids nor the strict / loose distinction matter and no id lookup is needed.
+    u64 key1 = ~0ull, du1 = 0;
+    u32 col1 = 0, n_cand = 0;
+    for (u32 e = rb + tile.thread_rank(); tile.any(e < re); e += TILE) {
+        if (e < re) {
+            const Arc a = ld_arc(arcs + e);
+            if (a.col != cur) {
+                const u64 du = ld_dist(dist + a.col);
+                const u64 ndb = (u64)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)du), a.w));
+                if (du < kInfBits && ndb == dv) { ++n_cand; key1 = a.street; du1 = du; col1 = a.col; }
+            }
+        }
+    }
+    u32 total = n_cand;
+    for (int o = TILE / 2; o > 0; o >>= 1) total += tile.shfl_xor(total, o);
+    if (total == 1u) {
+        // broadcast the single candidate from the lane that holds it
+        const u32 src = (u32)__ffs((int)tile.ballot(n_cand != 0u)) - 1u;
+        const u32 street = tile.shfl((u32)key1, src);
+        *col_out = tile.shfl(col1, src);
+        *du_out = tile.shfl(du1, src);
+        const u32 id_u = !WANT_ID ? 0u : orig ? __ldg(orig + *col_out) : *col_out;     // the walk only needs the street
+        return ((u64)id_u << 32) | street;
+    }
+    if (total == 0u) { *du_out = 0; *col_out = 0; return ~0ull; }
+    // ties: the full rule on the caller's ids
     const u32 id_cur = orig ? __ldg(orig + cur) : cur;
     u64 strict = ~0ull, loose = ~0ull, du_s = 0, du_l = 0;
     u32 col_s = 0, col_l = 0;
@@ -906,7 +933,7 @@ __global__ void __launch_bounds__(256) walk_kernel(WalkParams p)
         while (cur != root) {                                              // :83
             u64 du;
             u32 nxt;
-            const u64 key = canonical_pred<TILE>(tile, p.row_ptr, p.arcs, p.orig, dist, cur, dv, &nxt, &du);
+            const u64 key = canonical_pred<TILE, false>(tile, p.row_ptr, p.arcs, p.orig, dist, cur, dv, &nxt, &du);
             if (key == ~0ull || ++guard > p.V) { ++c_stuck; break; }
             if (tile.thread_rank() == 0) atomicAdd(p.load + (u32)key, p.volume);   // :86-88
             ++c_hops;
@@ -937,7 +964,7 @@ __global__ void __launch_bounds__(256) pred_kernel(const u32 *row_ptr, const Arc
         if (v != root && dv < kInfBits) {
             u64 du;
             u32 nxt;
-            const u64 key = canonical_pred<TILE>(tile, row_ptr, arcs, orig, dist, v, dv, &nxt, &du);
+            const u64 key = canonical_pred<TILE, true>(tile, row_ptr, arcs, orig, dist, v, dv, &nxt, &du);
             if (key != ~0ull) pr = (int32_t)(key >> 32);
         }
         if (tile.thread_rank() == 0) {
