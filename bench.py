@@ -8,8 +8,9 @@ and GTEPS; sim-day time against the CPU reference path).
 A step is one simulated day: K1 weights -> K2 one shortest-path tree per root -> K3 walk of every
 trip -> exchange (NCCL all-reduce of the uint32 load + cumulative merge).  Workload (config.workload):
 BASELINE.json configs[2], the synthetic 1024x1024 grid (V=1,048,576 S=2,095,104 A=4,190,208), 1M
-trips/day in total, goals = seeded 2 % node sample, one virtual rank (own trip stream and jam
-tolerance, streets4mpi.py:50-51,69,78) per GPU.
+trips/day per GPU (weak scaling: every GPU hosts one virtual rank with its own trip stream and jam
+tolerance, streets4mpi.py:50-51,69,78, and the ranks only meet in the daily all-reduce; --scaling strong
+divides one 1M-trip day over the GPUs instead), goals = seeded 2 % node sample.
 
 One JSON line on rank 0.  `value` = trips routed per second by the whole job with everything resident
 in HBM (CUDA events, max over ranks); `e2e` = the same through the reference-facing Python API with
@@ -50,11 +51,16 @@ def log(*a):
 # ----------------------------------------------------------------------------------------------
 # workload (identical for both arms)
 # ----------------------------------------------------------------------------------------------
-def make_workload(name, world):
+def make_workload(name, world, scaling="weak"):
+    """scaling == "weak": every GPU (= one virtual rank with its own trip stream and jam tolerance) routes the
+    workload's full day, the job routes world x that; "strong": the day's trips are divided over the ranks
+    like streets4mpi.py:69 divides number_of_residents."""
     from streets4mpi_b200 import synth
     rows, cols, trips_total = WORKLOADS[name]
     if TRIPS_OVERRIDE:
         trips_total = TRIPS_OVERRIDE
+    if scaling == "weak":
+        trips_total *= world
     arrays = synth.grid_arrays(rows, cols, seed=1) if rows else synth.planar_arrays(cols, seed=1)
     cats = synth.node_categories(arrays["node_ids"], seed=1, goal_fraction=0.02)
     per_rank = trips_total // world                       # streets4mpi.py:69
@@ -234,7 +240,7 @@ def reference_arm(args):
     line = {
         "impl": "reference", "metric": "routed_trips_per_sec", "value": value, "unit": "trips/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / max(1, args.steps),
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload + ": " + workload_text(args.workload), "root_mode": "origin (reference grouping)",
                    "sample": sample},
         "cpu_baseline": {"value": value, "unit": "trips/s", "cores": cores, "kind": "port", "sample": sample},
@@ -272,6 +278,8 @@ def gpu_arm(args):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"        # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
 
     import __graft_entry__ as ge
@@ -292,7 +300,7 @@ def gpu_arm(args):
         dev.set_option(k, float(v))
     settings["logging"] = None
 
-    arrays, cats, per_rank = make_workload(args.workload, world)
+    arrays, cats, per_rank = make_workload(args.workload, world, args.scaling)
     o, g, jam = rank_trips(arrays, cats, per_rank, rank)
     net = synth.network_from(arrays)
     t0 = time.perf_counter()
@@ -390,8 +398,9 @@ def gpu_arm(args):
         line = {
             "metric": "routed_trips_per_sec", "value": total_trips / (ms_max * 1e-3), "unit": "trips/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload + ": " + workload_text(args.workload),
+                       "trips_per_day": {"per_gpu": per_rank, "job": per_rank * world},
                        "root_mode": "%s (trees per day and GPU: %d)" % (mode, sim._sim.n_roots),
                        "virtual_ranks": world, "construction_every": args.construction_every,
                        "l2": "inputs larger than L2 (per-tree distance arrays, 8 B x V x trees in flight >> 126 MB)",
@@ -435,6 +444,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-trees-per-core", type=int, default=1)
     ap.add_argument("--trips", type=int, default=0, help="override the workload's trips per day")
+    ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
+                    help="weak: the workload's day per GPU (one virtual rank each); strong: the day divided over the GPUs")
     ap.add_argument("--construction-every", type=int, default=0, help="road adaptation every N days (0 = never)")
     args = ap.parse_args()
     global TRIPS_OVERRIDE
