@@ -97,10 +97,9 @@ int s4_ctx_sync(s4_ctx *ctx);
 /* Tunables (all have defaults): "delta_factor" (bucket width in mean arc
  * weights), "block_threads" (32|64|128|256|512|1024), "ctas_per_sm", "near_smem_entries", "queue_entries", "batch_roots",
  * "pool_bytes", "root_mode" (S4_ROOT_*), "walk_tile" (0 = auto|4|8|16|32),
- * "sssp_variant" (0 = barrier per relaxation round, 1 = barrier-free ring),
- * "preread" (0 = atomicMin straight away, 1 = filtering read then returning
- * atomicMin, 2 = filtering read decides the push and the minimum goes out as a
- * fire-and-forget reduction), "dist_l1", "lanes". */
+ * "preread" (1 = filtering read then returning atomicMin, 2 = the filtering
+ * read decides the push and the minimum goes out as a fire-and-forget
+ * reduction). */
 int s4_ctx_set_option(s4_ctx *ctx, const char *key, double value);
 int s4_ctx_get_option(s4_ctx *ctx, const char *key, double *value);
 /* name, SM count, bytes of HBM; name_out may be NULL */

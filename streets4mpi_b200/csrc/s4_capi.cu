@@ -54,16 +54,14 @@ struct Options {
     double delta_factor = 3.0;
     int block_threads = 0;          // 0 = from the graph (mean frontier width ~ V / hop depth)
     int ctas_per_sm = 0;            // 0 = as many CTAs as keep 1024 threads per SM
-    int near_smem_entries = 0;      // 0 = 4 entries per thread
+    int near_smem_entries = 0;      // 0 = 6 entries per thread
     int64_t queue_entries = 0;      // 0 = auto (from V)
     int64_t batch_roots = 0;        // 0 = auto (from pool_bytes)
     double pool_bytes = 64.0e9;
     int root_mode = S4_ROOT_ORIGIN;
     int walk_tile = 0;              // lanes per walking trip; 0 = from the graph's degrees
-    int sssp_variant = 0;           // 0 = barrier per relaxation round, 1 = barrier-free ring
-    int preread = 2;                // 0: atomic straight away; 1: filtering read, then returning atomic;
+    int preread = 2;                // 1: filtering read, then returning atomicMin;
                                     // 2: filtering read decides the push, minimum sent as RED (no wait)
-    int dist_l1 = 0;                // let L1 serve the filtering reads of dist[]
 };
 
 // Lifetime: handles are reference counted (sim -> graph -> ctx), so the host may
@@ -120,11 +118,11 @@ struct s4_graph {
     std::vector<int32_t> comp_of;
     std::vector<int64_t> comp_arcs, comp_nodes;
     int auto_block = 256;      // CTA width chosen from the graph's shape (see graph upload)
-    int auto_walk_tile = 8;    // lanes per walking trip: 4 when (almost) every node has at most 4 arcs
+    int auto_walk_tile = 8;    // lanes per walking trip
     // scratch shared by every simulation on this graph (sized lazily)
     DevBuf<u64> pool;          // slots * V
     int64_t pool_slots = 0;
-    DevBuf<u32> ws_v;          // per-CTA frontier workspace (nodes / distances)
+    DevBuf<u32> ws_v;          // per-CTA frontier workspace (entry words / distances), two lanes
     DevBuf<u64> ws_d;
     int ws_ctas = 0;
     u32 near_gcap = 0, far_cap = 0;
@@ -255,8 +253,7 @@ static void option_slot(Options &o, const char *key, int *kind, void **raw)
         {"near_smem_entries", 1, &o.near_smem_entries}, {"queue_entries", 2, &o.queue_entries},
         {"batch_roots", 2, &o.batch_roots},         {"pool_bytes", 0, &o.pool_bytes},
         {"root_mode", 1, &o.root_mode},             {"walk_tile", 1, &o.walk_tile},
-        {"sssp_variant", 1, &o.sssp_variant},       {"preread", 1, &o.preread},
-        {"dist_l1", 1, &o.dist_l1},
+        {"preread", 1, &o.preread},
     };
     for (auto &it : items)
         if (strcmp(it.k, key) == 0) { *kind = it.kind; *raw = it.p; return; }
@@ -282,7 +279,7 @@ extern "C" int s4_ctx_set_option(s4_ctx *ctx, const char *key, double value)
               (t.near_smem_entries == 0 || (t.near_smem_entries >= 32 && t.near_smem_entries <= 9000)) && t.queue_entries >= 0 &&
               t.batch_roots >= 0 && t.pool_bytes >= 0.0 && t.root_mode >= 0 && t.root_mode <= 2 &&
               (t.walk_tile == 0 || t.walk_tile == 4 || t.walk_tile == 8 || t.walk_tile == 16 || t.walk_tile == 32) &&
-              (t.sssp_variant == 0 || t.sssp_variant == 1);
+              (t.preread == 1 || t.preread == 2);
     if (!ok) return fail(S4_ERR_ARG, "option '%s': value %g out of range", key, value);
     ctx->opt = trial;
     return S4_OK;
@@ -459,7 +456,7 @@ extern "C" int s4_graph_upload(s4_ctx *ctx, int32_t V, int64_t S, const int32_t 
         g->auto_block = blk;
         int64_t wide = 0;
         for (int32_t i = 0; i < V; ++i) wide += (row_ptr[(size_t)i + 1] - row_ptr[(size_t)i]) > 4u;
-        g->auto_walk_tile = wide * 100 < (int64_t)V ? 4 : 8;
+        g->auto_walk_tile = wide * 2 > (int64_t)V ? 16 : 8;      // 8 lanes cover a road node's arcs in one step (measured: 4 is slower)
     }
     auto bail = [&](cudaError_t e, const char *what) {
         delete g;
@@ -515,15 +512,15 @@ extern "C" int s4_graph_dims(s4_graph *g, int32_t *V, int64_t *S, int64_t *A)
 // ---------------------------------------------------------------------------
 typedef void (*SsspKernel)(SsspParams);
 
-static SsspKernel pick_sssp(int block, int variant)
+static SsspKernel pick_sssp(int block)
 {
     switch (block) {
-        case 32: return variant ? sssp_async_kernel<32> : sssp_nearfar_kernel<32>;
-        case 64: return variant ? sssp_async_kernel<64> : sssp_nearfar_kernel<64>;
-        case 128: return variant ? sssp_async_kernel<128> : sssp_nearfar_kernel<128>;
-        case 256: return variant ? sssp_async_kernel<256> : sssp_nearfar_kernel<256>;
-        case 512: return variant ? sssp_async_kernel<512> : sssp_nearfar_kernel<512>;
-        case 1024: return variant ? sssp_async_kernel<1024> : sssp_nearfar_kernel<1024>;
+        case 32: return sssp_nearfar_kernel<32>;
+        case 64: return sssp_nearfar_kernel<64>;
+        case 128: return sssp_nearfar_kernel<128>;
+        case 256: return sssp_nearfar_kernel<256>;
+        case 512: return sssp_nearfar_kernel<512>;
+        case 1024: return sssp_nearfar_kernel<1024>;
     }
     return nullptr;
 }
@@ -550,23 +547,13 @@ static int plan_sssp(s4_graph *g, SsspLaunch *L)
         const int64_t per_lane = std::max<int64_t>(1, slots / 2);
         while (block < 1024 && (int64_t)g->ctx->prop.multiProcessorCount * std::min(32, 1024 / block) > per_lane) block *= 2;
     }
-    const int near_entries = o.near_smem_entries ? o.near_smem_entries : std::max(128, 4 * block);
+    const int near_entries = o.near_smem_entries ? o.near_smem_entries : std::max(128, 6 * block);     // measured on cfg3
     const int ctas = o.ctas_per_sm ? o.ctas_per_sm : std::min(32, std::max(1, 1024 / block));
-    L->fn = pick_sssp(block, o.sssp_variant);
+    L->fn = pick_sssp(block);
     if (!L->fn) return fail(S4_ERR_ARG, "no SSSP kernel for block=%d", block);
     L->block = block;
-    if (o.sssp_variant) {
-        // one ring of 2 * near_entries slots rounded down to a power of two (same shared-memory budget),
-        // never smaller than twice the worst-case concurrent push of the CTA
-        u32 want = (u32)near_entries * 2u, rcap = 1u;
-        while (rcap * 2u <= want) rcap *= 2u;
-        while (rcap < (u32)block * kEllWidth * 2u) rcap *= 2u;
-        L->scap = rcap;
-        L->smem = (size_t)rcap * (sizeof(u64) + sizeof(u32));
-    } else {
-        L->scap = (u32)near_entries;
-        L->smem = (size_t)2 * L->scap * (sizeof(u64) + sizeof(u32));
-    }
+    L->scap = (u32)near_entries;
+    L->smem = (size_t)2 * L->scap * (sizeof(u64) + sizeof(u32));
     CU(cudaFuncSetAttribute((const void *)L->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L->smem));
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)L->fn, L->block, L->smem));
@@ -628,7 +615,6 @@ static int launch_sssp(s4_graph *g, const SsspLaunch &L, const Arc *ell, const A
     p.near_gcap = g->near_gcap;
     p.far_cap = g->far_cap;
     p.preread = (u32)g->ctx->opt.preread;
-    p.dist_l1 = (u32)g->ctx->opt.dist_l1;
     p.counters = counters;
     const int grid = std::min(L.grid, std::max(1, n_roots));
     L.fn<<<grid, L.block, L.smem, st>>>(p);

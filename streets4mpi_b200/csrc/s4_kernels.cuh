@@ -57,9 +57,6 @@ struct __align__(16) Arc {
 };
 
 __device__ __forceinline__ u64 ld_dist(const u64 *p) { return __ldcg(p); }   // L2-coherent with the atomics
-// filtering read: distances only ever decrease, so a stale (larger) value from L1 is conservative --
-// it can cause a superfluous atomicMin or the expansion of a superseded entry, never a wrong result
-__device__ __forceinline__ u64 ld_dist_filter(const u64 *p, u32 via_l1) { return via_l1 ? __ldca(p) : __ldcg(p); }
 __device__ __forceinline__ u32 hi32(u64 x) { return (u32)(x >> 32); }
 
 __device__ __forceinline__ Arc ld_arc(const Arc *p)
@@ -203,8 +200,7 @@ struct SsspParams {
     u32 near_scap;          // entries per near queue in shared memory
     u32 near_gcap;          // spill entries per near queue in global memory
     u32 far_cap;            // entries per far pile
-    u32 preread;            // 1: read dist[head] first and only issue the atomic when it can win; 0: atomic straight away
-    u32 dist_l1;            // 1: the filtering reads of dist[] may be served by L1 (a stale, larger value only costs a wasted atomic)
+    u32 preread;            // 1: filtering read, then returning atomicMin; 2: filtering read decides the push, RED.MIN
     u64 *counters;
 };
 
@@ -254,7 +250,7 @@ __device__ __forceinline__ bool expand_entry(const Arc *__restrict__ ell, u64 *d
         pd[j] = (u64)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)du), a[j].w));
         if ((u32)j == skip) pd[j] = kInfBits;
         old[j] = kInfBits;
-        if (preread && pd[j] < kInfBits) {
+        if (pd[j] < kInfBits) {                              // padding slots have w == +inf
             if ((pv[j] >> 2) == (u >> 2)) old[j] = pick4(sec, pv[j] & 3u);
             else old[j] = ld_dist(dist + pv[j]);
         }
@@ -532,282 +528,6 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024
 #pragma unroll
     for (int j = 0; j < 7; ++j) {
         u64 v = vals[j];
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0 && v) atomicAdd(p.counters + ids[j], v);
-    }
-}
-
-// ---------------------------------------------------------------------------
-// K2, barrier-free variant.  Same data layout, same entries, same fixed point as
-// sssp_nearfar_kernel, but inside a bucket the warps of the CTA do not meet at a
-// barrier per round: the near queue is one ring in shared memory, every warp
-// claims up to 32 ready entries (CAS on the head), expands them and appends the
-// improved heads to the same ring (reserve on the tail, per-slot ready flag), so
-// a warp never waits for the slowest memory access of another warp.  The bucket
-// is finished when every reserved entry has been processed (done == tail); only
-// then the CTA synchronises, splits the far pile and refills the ring.  A full
-// ring simply diverts pushes to the far pile (they come back at a later split).
-// ---------------------------------------------------------------------------
-static constexpr u32 kSlotEmpty = 0xFFFFFFFFu;
-
-__device__ __forceinline__ u32 ld_vol(const u32 *p) { return *reinterpret_cast<const volatile u32 *>(p); }
-
-struct Ring {
-    u32 *rv; u64 *rd;       // rcap slots (power of two); rv == kSlotEmpty: not written yet
-    u32 mask;               // rcap - 1
-    u32 limit;              // pushes go to the far pile once tail - done would exceed this
-    u32 *head, *tail, *done;
-};
-
-// Warp-cooperative append: kind[j] 1 = ring, 2 = far pile.  Ring candidates fall back to the
-// far pile when the ring is (conservatively) full.
-template <int N>
-__device__ __forceinline__ void warp_push_async(u32 (&kind)[N], const u32 (&pv)[N], const u64 (&pd)[N], u32 lane,
-                                                const Ring &R, u32 *far_v, u64 *far_d, u32 *far_cnt, u32 *far_min,
-                                                u32 fcap, u32 *overflow, u64 &c_push)
-{
-    u32 packed = 0;
-#pragma unroll
-    for (int j = 0; j < N; ++j) packed += (kind[j] == 1u ? 1u : 0u) + (kind[j] == 2u ? 0x10000u : 0u);
-    u32 incl = packed;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
-        if ((int)lane >= o) incl += t;
-    }
-    u32 total = __shfl_sync(0xffffffffu, incl, 31);
-    if (total == 0u) return;                                   // warp-uniform
-    u32 base_n = 0, ring_ok = 1;
-    if (total & 0xFFFFu) {
-        if (lane == 31) {
-            const u32 t = ld_vol(R.tail), d = ld_vol(R.done);
-            if (t - d + (total & 0xFFFFu) > R.limit) ring_ok = 0u;
-            else base_n = atomicAdd(R.tail, total & 0xFFFFu);
-        }
-        ring_ok = __shfl_sync(0xffffffffu, ring_ok, 31);
-        base_n = __shfl_sync(0xffffffffu, base_n, 31);
-    }
-    u32 excl = incl - packed;
-    if (!ring_ok) {
-        // ring full: every candidate of this warp goes to the far pile
-        excl = (excl & 0xFFFFu) + (excl >> 16);
-        total = ((total & 0xFFFFu) + (total >> 16)) << 16;
-#pragma unroll
-        for (int j = 0; j < N; ++j) if (kind[j] == 1u) kind[j] = 2u;
-        excl <<= 16;
-    }
-    u32 base_f = 0;
-    if (total >> 16) {
-        u32 mymin = 0xFFFFFFFFu;
-#pragma unroll
-        for (int j = 0; j < N; ++j) if (kind[j] == 2u) mymin = min(mymin, hi32(pd[j]));
-        const u32 wmin = __reduce_min_sync(0xffffffffu, mymin);
-        if (lane == 31) { base_f = atomicAdd(far_cnt, total >> 16); atomicMin(far_min, wmin); }
-        base_f = __shfl_sync(0xffffffffu, base_f, 31);
-    }
-    u32 on = base_n + (excl & 0xFFFFu), of = base_f + (excl >> 16);
-#pragma unroll
-    for (int j = 0; j < N; ++j) {
-        if (kind[j] == 1u) {
-            const u32 slot = on & R.mask;
-            while (ld_vol(R.rv + slot) != kSlotEmpty) { }       // previous lap's entry not read yet (never in practice)
-            R.rd[slot] = pd[j];
-            __threadfence_block();                              // distance before the ready flag
-            *reinterpret_cast<volatile u32 *>(R.rv + slot) = pv[j];
-            ++on; ++c_push;
-        } else if (kind[j] == 2u) {
-            if (of < fcap) { far_v[of] = pv[j]; far_d[of] = pd[j]; } else *overflow = 1u;
-            ++of; ++c_push;
-        }
-    }
-}
-
-template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024 / BLOCK : 1)) sssp_async_kernel(SsspParams p)
-{
-    static_assert(BLOCK % 32 == 0, "whole warps");
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const u32 rcap = p.near_scap;                  // power of two
-    const u32 fcap = p.far_cap;
-    u64 *rd = reinterpret_cast<u64 *>(smem_raw);
-    u32 *rv = reinterpret_cast<u32 *>(rd + rcap);
-    __shared__ u32 s_head, s_tail, s_done;
-    __shared__ u32 s_far_cnt[2];
-    __shared__ u32 s_far_min[2];
-    __shared__ int s_root_idx;
-    __shared__ u32 s_overflow;
-    __shared__ u32 s_changed;
-
-    const u32 tid = threadIdx.x;
-    const u32 lane = tid & 31u;
-    const u32 V = p.V;
-    const size_t ws_stride = (size_t)2 * p.near_gcap + (size_t)2 * fcap;
-    u32 *wv = p.ws_v + (size_t)blockIdx.x * ws_stride + 2 * (size_t)p.near_gcap;   // the two far piles
-    u64 *wd = p.ws_d + (size_t)blockIdx.x * ws_stride + 2 * (size_t)p.near_gcap;
-    Ring R;
-    R.rv = rv; R.rd = rd; R.mask = rcap - 1u;
-    R.limit = rcap - (BLOCK / 32) * 32u * kEllWidth;          // room for one concurrent push of every warp
-    R.head = &s_head; R.tail = &s_tail; R.done = &s_done;
-
-    double delta = p.delta_scale * (*p.wsum);
-    if (!(delta > 0.0)) delta = 0.0;
-    for (u32 i = tid; i < rcap; i += BLOCK) rv[i] = kSlotEmpty;
-
-    u64 c_relax = 0, c_pop = 0, c_stale = 0, c_push = 0, c_adv = 0, c_round = 0, c_sweep = 0;
-
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) s_root_idx = (int)atomicAdd(p.work_counter, 1u);
-        __syncthreads();
-        const int ri = s_root_idx;
-        if (ri >= p.n_roots) break;
-        u64 *dist = p.dist_pool + (size_t)ri * p.slot_stride;
-        const u32 root = (u32)p.roots[ri];
-        {
-            ulonglong2 *d2 = reinterpret_cast<ulonglong2 *>(dist);
-            const u32 n2 = (u32)(p.slot_stride >> 1);
-            const ulonglong2 inf2 = make_ulonglong2(kInfBits, kInfBits);
-            for (u32 i = tid; i < n2; i += BLOCK) d2[i] = inf2;
-        }
-        if (tid == 0) {
-            s_head = 0u; s_tail = 1u; s_done = 0u;
-            s_far_cnt[0] = 0u; s_far_cnt[1] = 0u;
-            s_far_min[0] = 0xFFFFFFFFu; s_far_min[1] = 0xFFFFFFFFu;
-            s_overflow = 0u;
-            rd[0] = 0ull; rv[0] = root | kNoSkip;
-        }
-        __syncthreads();
-        if (tid == 0) dist[root] = 0ull;
-        __syncthreads();
-
-        u32 f = 0;
-        u32 thr_hi = hi32((u64)__double_as_longlong(delta));
-
-        for (;;) {
-            // ------------------------- bucket phase: warps run free -------------------------
-            u32 *const fv = wv + (size_t)f * fcap;
-            u64 *const fd = wd + (size_t)f * fcap;
-            for (;;) {
-                u32 start = 0, n = 0;
-                if (lane == 0) {
-                    for (;;) {
-                        const u32 h = ld_vol(&s_head), t = ld_vol(&s_tail);
-                        if (t != h) {
-                            const u32 k = min(32u, t - h);
-                            if (atomicCAS(&s_head, h, h + k) == h) { start = h; n = k; break; }
-                            continue;
-                        }
-                        if (ld_vol(&s_done) == t && ld_vol(&s_tail) == t) { n = 0xFFFFFFFFu; break; }   // bucket drained
-                        __nanosleep(40);
-                    }
-                }
-                start = __shfl_sync(0xffffffffu, start, 0);
-                n = __shfl_sync(0xffffffffu, n, 0);
-                if (n == 0xFFFFFFFFu) break;
-                ++c_round;
-                bool valid = lane < n;
-                u32 u = 0;
-                u64 du = 0;
-                u32 kind[kEllWidth], pv[kEllWidth];
-                u64 pd[kEllWidth];
-#pragma unroll
-                for (int j = 0; j < kEllWidth; ++j) { kind[j] = 0u; pv[j] = 0u; pd[j] = 0ull; }
-                bool ovf = false;
-                if (valid) {
-                    const u32 slot = (start + lane) & R.mask;
-                    while ((u = ld_vol(rv + slot)) == kSlotEmpty) { }           // reserved, being written
-                    __threadfence_block();
-                    du = *reinterpret_cast<volatile u64 *>(rd + slot);
-                    *reinterpret_cast<volatile u32 *>(rv + slot) = kSlotEmpty;  // recycle before `done` moves
-                    valid = expand_entry(p.ell, dist, u, du, thr_hi, p.preread, kind, pv, pd, ovf);
-                    if (valid) { ++c_pop; c_relax += kEllWidth; } else ++c_stale;
-                }
-                warp_push_async<kEllWidth>(kind, pv, pd, lane, R, fv, fd, &s_far_cnt[f], &s_far_min[f], fcap, &s_overflow, c_push);
-                if (__any_sync(0xffffffffu, ovf)) {
-                    u32 e = 0, re = 0;
-                    if (ovf) { e = __ldg(p.row_ptr + (u & kNodeMask)) + kEllWidth; re = __ldg(p.row_ptr + (u & kNodeMask) + 1); }
-                    while (__any_sync(0xffffffffu, e < re)) {
-                        u32 k1[1] = {0u}, v1[1] = {0u};
-                        u64 d1[1] = {0ull};
-                        if (e < re) {
-                            const Arc x = ld_arc(p.arcs + e);
-                            v1[0] = x.col | kNoSkip;
-                            d1[0] = (u64)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)du), x.w));
-                            if (d1[0] < ld_dist(dist + x.col)) {
-                                const u64 o2 = atomicMin(dist + x.col, d1[0]);
-                                if (d1[0] < o2) k1[0] = hi32(d1[0]) <= thr_hi ? 1u : 2u;
-                            }
-                            ++c_relax;
-                            ++e;
-                        }
-                        warp_push_async<1>(k1, v1, d1, lane, R, fv, fd, &s_far_cnt[f], &s_far_min[f], fcap, &s_overflow, c_push);
-                    }
-                }
-                __syncwarp();
-                if (lane == 0) { __threadfence_block(); atomicAdd(&s_done, n); }
-            }
-            __syncthreads();                                            // bucket drained, ring empty
-            // ------------------------- advance the bucket -------------------------
-            const u32 nf_raw = s_far_cnt[f];
-            if (nf_raw == 0u) break;                                    // tree complete
-            const u32 nf = nf_raw < fcap ? nf_raw : fcap;
-            const u32 far_min_hi = s_far_min[f];
-            ++c_adv;
-            const double lo = __longlong_as_double((long long)((u64)far_min_hi << 32));
-            thr_hi = hi32((u64)__double_as_longlong(__dadd_rn(lo, delta)));
-            const u32 fo = f ^ 1u;
-            const u32 *srcv = wv + (size_t)f * fcap;
-            const u64 *srcd = wd + (size_t)f * fcap;
-            for (u32 base = 0; base < nf; base += BLOCK) {
-                const u32 i = base + tid;
-                u32 k1[1] = {0u}, v1[1] = {0u};
-                u64 d1[1] = {0ull};
-                if (i < nf) {
-                    v1[0] = srcv[i];
-                    d1[0] = srcd[i];
-                    k1[0] = hi32(d1[0]) <= thr_hi ? 1u : 2u;
-                }
-                warp_push_async<1>(k1, v1, d1, lane, R, wv + (size_t)fo * fcap, wd + (size_t)fo * fcap, &s_far_cnt[fo],
-                                   &s_far_min[fo], fcap, &s_overflow, c_push);
-            }
-            __syncthreads();
-            if (tid == 0) { s_far_cnt[f] = 0u; s_far_min[f] = 0xFFFFFFFFu; }
-            f = fo;
-            __syncthreads();
-        }
-
-        if (s_overflow) {
-            for (;;) {
-                __syncthreads();
-                if (tid == 0) s_changed = 0u;
-                __syncthreads();
-                ++c_sweep;
-                bool any = false;
-                for (u32 u = tid; u < V; u += BLOCK) {
-                    const u64 du = ld_dist(dist + u);
-                    if (du >= kInfBits) continue;
-                    const u32 rb = __ldg(p.row_ptr + u), re = __ldg(p.row_ptr + u + 1);
-                    for (u32 e = rb; e < re; ++e) {
-                        const Arc x = ld_arc(p.arcs + e);
-                        const u64 ndb = (u64)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)du), x.w));
-                        if (ndb < ld_dist(dist + x.col)) {
-                            atomicMin(dist + x.col, ndb);
-                            any = true;
-                        }
-                    }
-                }
-                if (any) s_changed = 1u;
-                __syncthreads();
-                if (!s_changed) break;
-            }
-        }
-    }
-
-    u64 vals[7] = {c_relax, c_pop, c_stale, c_push, tid == 0 ? c_adv : 0, c_round, tid == 0 ? c_sweep : 0};
-    const int ids[7] = {C_ARCS_RELAXED, C_NODES_POPPED, C_STALE_POPS, C_PUSHES, C_ADVANCES, C_ROUNDS, C_FALLBACK_SWEEPS};
-#pragma unroll
-    for (int j = 0; j < 7; ++j) {
-        u64 v = j == 5 ? (lane == 0 ? vals[j] : 0) : vals[j];
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         if (lane == 0 && v) atomicAdd(p.counters + ids[j], v);
     }

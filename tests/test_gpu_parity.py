@@ -145,8 +145,8 @@ def test_road_construction_golden(dev, phys):
 @pytest.mark.parametrize("shape", ["grid", "planar"])
 @pytest.mark.parametrize("opts", [dict(), dict(block_threads=256, ctas_per_sm=4, delta_factor=0.5),
                                   dict(block_threads=1024, delta_factor=8.0, near_smem_entries=64),
-                                  dict(delta_factor=0.0), dict(sssp_variant=0), dict(sssp_variant=0, near_smem_entries=64),
-                                  dict(sssp_variant=1, block_threads=256, near_smem_entries=64)])
+                                  dict(delta_factor=0.0), dict(preread=1), dict(preread=1, near_smem_entries=64),
+                                  dict(block_threads=32, near_smem_entries=32, delta_factor=1.0)])
 @pytest.mark.parametrize("ranked", [False, True])
 def test_sssp_dist_and_pred_vs_oracle(dev, shape, opts, ranked):
     """Single trees: distances bit-equal to Dijkstra, predecessors equal under the canonical rule;
@@ -331,8 +331,8 @@ def test_root_mode_invariance_unique_paths(dev, phys):
     g.close()
 
 
-@pytest.mark.parametrize("variant", [0, 1])
-def test_queue_overflow_falls_back_to_sweeps(dev, phys, variant):
+@pytest.mark.parametrize("preread", [1, 2])
+def test_queue_overflow_falls_back_to_sweeps(dev, phys, preread):
     """Starve the frontier queues: entries are dropped, the Bellman-Ford safety net must
     still deliver exact distances."""
     from oracle import ctwin
@@ -341,9 +341,9 @@ def test_queue_overflow_falls_back_to_sweeps(dev, phys, variant):
     V = 64 * 64
     rng = np.random.default_rng(4)
     w = rng.uniform(0.1, 10.0, len(arr["u"]))
-    old = {k: dev.get_option(k) for k in ("near_smem_entries", "queue_entries", "delta_factor", "sssp_variant")}
+    old = {k: dev.get_option(k) for k in ("near_smem_entries", "queue_entries", "delta_factor", "preread")}
     try:
-        dev.set_option("sssp_variant", variant)
+        dev.set_option("preread", preread)
         dev.set_option("near_smem_entries", 64)
         dev.set_option("queue_entries", 16)
         dev.set_option("delta_factor", 50.0)
