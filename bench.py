@@ -357,6 +357,8 @@ def gpu_arm(args):
     # ---- end to end through the reference-facing API: host arrays every day (streets4mpi.py:93-100)
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     from streets4mpi_b200 import merge_arrays
+    sim.traffic_load = sim.traffic_load                     # the driver holds host copies from "yesterday":
+    sim.cumulative_traffic_load = sim.cumulative_traffic_load   # every timed day starts with their upload
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
