@@ -60,6 +60,7 @@ struct Options {
     double pool_bytes = 64.0e9;
     int root_mode = S4_ROOT_ORIGIN;
     int walk_tile = 0;              // lanes per walking trip; 0 = from the graph's degrees
+    int lanes = 2;                  // concurrent (SSSP launch -> walk) lanes per day; 1 = strictly serial kernels
     int preread = 2;                // 1: filtering read, then returning atomicMin;
                                     // 2: filtering read decides the push, minimum sent as RED (no wait)
 };
@@ -253,7 +254,7 @@ static void option_slot(Options &o, const char *key, int *kind, void **raw)
         {"near_smem_entries", 1, &o.near_smem_entries}, {"queue_entries", 2, &o.queue_entries},
         {"batch_roots", 2, &o.batch_roots},         {"pool_bytes", 0, &o.pool_bytes},
         {"root_mode", 1, &o.root_mode},             {"walk_tile", 1, &o.walk_tile},
-        {"preread", 1, &o.preread},
+        {"preread", 1, &o.preread},                 {"lanes", 1, &o.lanes},
     };
     for (auto &it : items)
         if (strcmp(it.k, key) == 0) { *kind = it.kind; *raw = it.p; return; }
@@ -279,7 +280,7 @@ extern "C" int s4_ctx_set_option(s4_ctx *ctx, const char *key, double value)
               (t.near_smem_entries == 0 || (t.near_smem_entries >= 32 && t.near_smem_entries <= 9000)) && t.queue_entries >= 0 &&
               t.batch_roots >= 0 && t.pool_bytes >= 0.0 && t.root_mode >= 0 && t.root_mode <= 2 &&
               (t.walk_tile == 0 || t.walk_tile == 4 || t.walk_tile == 8 || t.walk_tile == 16 || t.walk_tile == 32) &&
-              (t.preread == 1 || t.preread == 2);
+              (t.preread == 1 || t.preread == 2) && (t.lanes == 1 || t.lanes == 2);
     if (!ok) return fail(S4_ERR_ARG, "option '%s': value %g out of range", key, value);
     ctx->opt = trial;
     return S4_OK;
@@ -971,8 +972,9 @@ extern "C" int s4_sim_step(s4_sim *sim)
     // latency-bound pointer chase) hides under the other lane's SSSP.
     const int64_t D = sim->D;
     const int64_t slots = std::max<int64_t>(1, g->pool_slots);
-    const bool split = D > slots && slots >= 2;
-    const int64_t B = split ? slots / 2 : slots;
+    const bool halves = D > slots && slots >= 2;                   // launch size: half the pool
+    const bool split = halves && ctx->opt.lanes >= 2;              // ... and the halves run as concurrent lanes
+    const int64_t B = halves ? slots / 2 : slots;
     const int64_t n_batches = (D + B - 1) / B;
     if (n_batches > 0) {
         CU(g->work_counters.ensure((size_t)std::max<int64_t>(n_batches, 1024)));
