@@ -189,3 +189,26 @@ def test_streets4mpi_on_osm_file_matches_port(tmp_path, residents, every):
         os.chdir(cwd)
         settings.clear(); settings.update(old)
         device_settings.clear(); device_settings.update(old_dev)
+
+
+def test_visualization_speed_modes(tmp_path):
+    """IDEAL_SPEED / ACTUAL_SPEED evaluate calculate_driving_speed for every street on the device."""
+    from array import array as _array
+    from streets4mpi_b200 import persistence, synth
+    from streets4mpi_b200.osmdata import GraphBuilder
+    from streets4mpi_b200.visualization import Visualization
+    osm = str(tmp_path / "t.osm")
+    synth.write_osm_xml(osm, rows=6, cols=7, seed=2)
+    net = GraphBuilder(osm).build_street_network()
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        persistence.persist_write("street_network_1.s4mpi", net)
+        persistence.persist_write("traffic_load_1.s4mpi", _array("I", [3] * net.street_index), is_array=True)
+        for mode in ("IDEAL_SPEED", "ACTUAL_SPEED"):
+            v = Visualization("^street_network_[0-9]+.s4mpi$", "^traffic_load_[0-9]+.s4mpi$", mode=mode, verbose=False)
+            assert v.visualize() == ["traffic_load_1.png"]
+            vals = v._street_values(_array("I", [3] * net.street_index), 3)
+            assert len(vals) == net.street_index and 0.0 < max(vals) <= 1.0
+    finally:
+        os.chdir(cwd)

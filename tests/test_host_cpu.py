@@ -224,3 +224,39 @@ def test_osm_ingest_rules(tmp_path):
     assert b.get_all_child_nodes(123456789) == set()
     flat = net.flat()
     assert flat.locality_rank() is not None and sorted(flat.locality_rank().tolist()) == list(range(120))
+
+
+def test_visualization_modes_without_gpu(tmp_path):
+    """The offline heat maps read the .s4mpi files and write one PNG per day (no device needed for the
+    load / speed-limit / component modes)."""
+    from array import array as _array
+    from PIL import Image
+    from streets4mpi_b200 import persistence, synth
+    from streets4mpi_b200.osmdata import GraphBuilder
+    from streets4mpi_b200.visualization import Visualization
+    osm = str(tmp_path / "t.osm")
+    synth.write_osm_xml(osm, rows=8, cols=9, seed=1)
+    net = GraphBuilder(osm).build_street_network()
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        persistence.persist_write("street_network_1.s4mpi", net)
+        rng = np.random.default_rng(0)
+        for day in (1, 2):
+            persistence.persist_write("traffic_load_%d.s4mpi" % day,
+                                      _array("I", rng.integers(0, 50, net.street_index).tolist()), is_array=True)
+        for mode, cm in (("TRAFFIC_LOAD", "HEATMAP"), ("MAX_SPEED", "MONOCHROME"), ("COMPONENTS", "HEATMAP")):
+            out = Visualization("^street_network_[0-9]+.s4mpi$", "^traffic_load_[0-9]+.s4mpi$", mode=mode,
+                                color_mode=cm, verbose=False).visualize()
+            assert out == ["traffic_load_1.png", "traffic_load_2.png"]
+            img = Image.open(out[0])
+            assert img.size[0] > 500 and img.size[1] > 500 and len(img.getcolors(1 << 20)) > 3
+        v = Visualization("x", "y", verbose=False)
+        assert v.value_to_color(0.0) == "hsl(260,100%,5%)" and v.value_to_color(1.0) == "hsl(0,100%,50%)"
+        assert Visualization("x", "y", color_mode="MONOCHROME", verbose=False).value_to_color(0.5) == (135, 135, 135, 0)
+        comps = Visualization.calculate_components(net)
+        assert set(comps.values()) == {1}
+        with pytest.raises(ValueError):
+            Visualization("x", "y", mode="NOPE")
+    finally:
+        os.chdir(cwd)
