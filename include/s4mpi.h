@@ -100,7 +100,8 @@ int s4_ctx_sync(s4_ctx *ctx);
  * "preread" (1 = filtering read then returning atomicMin, 2 = the filtering
  * read decides the push and the minimum goes out as a fire-and-forget
  * reduction), "lanes" (2 = a day's batches alternate between two concurrent
- * launch lanes, 1 = strictly serial kernels, e.g. for per-kernel timing). */
+ * launch lanes, 1 = strictly serial kernels, e.g. for per-kernel timing),
+ * "adaptive_delta" (1 = the bucket width follows the width of the wave). */
 int s4_ctx_set_option(s4_ctx *ctx, const char *key, double value);
 int s4_ctx_get_option(s4_ctx *ctx, const char *key, double *value);
 /* name, SM count, bytes of HBM; name_out may be NULL */

@@ -61,6 +61,7 @@ struct Options {
     int root_mode = S4_ROOT_ORIGIN;
     int walk_tile = 0;              // lanes per walking trip; 0 = from the graph's degrees
     int lanes = 2;                  // concurrent (SSSP launch -> walk) lanes per day; 1 = strictly serial kernels
+    int adaptive_delta = 1;         // widen / narrow the bucket with the wave
     int preread = 2;                // 1: filtering read, then returning atomicMin;
                                     // 2: filtering read decides the push, minimum sent as RED (no wait)
 };
@@ -255,6 +256,7 @@ static void option_slot(Options &o, const char *key, int *kind, void **raw)
         {"batch_roots", 2, &o.batch_roots},         {"pool_bytes", 0, &o.pool_bytes},
         {"root_mode", 1, &o.root_mode},             {"walk_tile", 1, &o.walk_tile},
         {"preread", 1, &o.preread},                 {"lanes", 1, &o.lanes},
+        {"adaptive_delta", 1, &o.adaptive_delta},
     };
     for (auto &it : items)
         if (strcmp(it.k, key) == 0) { *kind = it.kind; *raw = it.p; return; }
@@ -616,6 +618,7 @@ static int launch_sssp(s4_graph *g, const SsspLaunch &L, const Arc *ell, const A
     p.near_gcap = g->near_gcap;
     p.far_cap = g->far_cap;
     p.preread = (u32)g->ctx->opt.preread;
+    p.adaptive = (u32)g->ctx->opt.adaptive_delta;
     p.counters = counters;
     const int grid = std::min(L.grid, std::max(1, n_roots));
     L.fn<<<grid, L.block, L.smem, st>>>(p);

@@ -201,6 +201,7 @@ struct SsspParams {
     u32 near_gcap;          // spill entries per near queue in global memory
     u32 far_cap;            // entries per far pile
     u32 preread;            // 1: filtering read, then returning atomicMin; 2: filtering read decides the push, RED.MIN
+    u32 adaptive;           // 1: the bucket width follows the width of the wave
     u64 *counters;
 };
 
@@ -349,6 +350,8 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024
     __shared__ int s_root_idx;
     __shared__ u32 s_overflow;
     __shared__ u32 s_changed;
+    __shared__ u32 s_bucket_rounds;     // relaxation rounds since the last bucket advance
+    __shared__ u32 s_bucket_entries;    // entries popped in them
 
     const u32 tid = threadIdx.x;
     const u32 lane = tid & 31u;
@@ -387,12 +390,14 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024
             s_far_cnt[0] = 0u; s_far_cnt[1] = 0u;
             s_far_min[0] = 0xFFFFFFFFu; s_far_min[1] = 0xFFFFFFFFu;
             s_overflow = 0u;
+            s_bucket_rounds = 0u; s_bucket_entries = 0u;
             sv0[0] = root | kNoSkip; sd0[0] = 0ull;
         }
         __syncthreads();
         if (tid == 0) dist[root] = 0ull;                   // after the fill
         __syncthreads();
 
+        double dmul = 1.0;  // adaptive multiplier of the bucket width
         u32 c = 0;          // index of the current near counter
         u32 b = 0;          // current near buffer
         u32 f = 0;          // current far pile (push target)
@@ -403,7 +408,11 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024
             if (n > 0) {
                 // ------------------------- relaxation round -------------------------
                 const u32 cn = c == 2 ? 0 : c + 1;
-                if (tid == 0) s_cnt[cn == 2 ? 0 : cn + 1] = 0u;        // counter of the round after next
+                if (tid == 0) {
+                    s_cnt[cn == 2 ? 0 : cn + 1] = 0u;                  // counter of the round after next
+                    s_bucket_rounds += 1u;
+                    s_bucket_entries += n;
+                }
                 const Queue qc = near_q(b);
                 const Queue qn = near_q(b ^ 1u);
                 u32 *const fv = far_v(f);
@@ -466,7 +475,16 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024
             ++c_adv;
             // new threshold: smallest (lower bound of a) distance in the pile + delta
             const double lo = __longlong_as_double((long long)((u64)far_min_hi << 32));
-            thr_hi = hi32((u64)__double_as_longlong(__dadd_rn(lo, delta)));
+            // bucket width follows the wave: widen while the rounds of a bucket leave most of the CTA idle,
+            // narrow again when a bucket floods it (priority order pays off once there is enough parallelism)
+            if (p.adaptive) {
+                const u32 br = s_bucket_rounds, be = s_bucket_entries;
+                if (br > 0u) {
+                    if (be < br * (BLOCK / 2u) && dmul < 16.0) dmul *= 1.5;
+                    else if (be > br * (BLOCK * 4u) && dmul > 1.0) dmul *= (1.0 / 1.5);
+                }
+            }
+            thr_hi = hi32((u64)__double_as_longlong(__dadd_rn(lo, delta * dmul)));
             const u32 fo = f ^ 1u;
             const u32 *srcv = far_v(f);
             const u64 *srcd = far_d(f);
@@ -487,7 +505,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024
                              &s_far_min[fo], fcap, &s_overflow, c_push);
             }
             __syncthreads();
-            if (tid == 0) { s_far_cnt[f] = 0u; s_far_min[f] = 0xFFFFFFFFu; }
+            if (tid == 0) { s_far_cnt[f] = 0u; s_far_min[f] = 0xFFFFFFFFu; s_bucket_rounds = 0u; s_bucket_entries = 0u; }
             f = fo;
             // no barrier needed: pile f^1 is not a push target until the next advance,
             // and a relaxation round (with its barrier) always intervenes.
