@@ -378,3 +378,90 @@ def test_c_abi_error_behaviour(dev, phys):
     assert sim.get_load().tolist() == [0, 0]
     sim.close()
     g.close()
+
+
+def test_degenerate_graphs(dev, phys):
+    """Single node without streets, a lone self loop, an origin == goal trip, a trip into another component."""
+    from streets4mpi_b200 import engine
+    g = engine.DeviceGraph(dev, 1, np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0), np.zeros(0, np.int32))
+    sim = engine.DeviceSim(g, [0, 0], [0, 0], 0.5, phys)
+    sim.step()
+    assert sim.get_load().tolist() == [] and sim.counters()["hops"] == 0
+    dist, pred = g.sssp(np.zeros(0), 0)
+    assert dist.tolist() == [0.0] and pred.tolist() == [-1]
+    sim.close()
+    g.close()
+    g = engine.DeviceGraph(dev, 4, [1, 2], [1, 3], [5.0, 7.0], [30, 50])           # self loop on 1, street 2-3, node 0 isolated
+    sim = engine.DeviceSim(g, [2, 0, 1, 3], [3, 2, 1, 3], 0.1, phys)
+    for _ in range(2):
+        sim.step()
+        assert sim.get_load().tolist() == [0, 1]
+        sim.commit_total()
+    c = sim.counters()
+    assert c["trips_unreachable"] == 2 and c["trips_routed"] == 8 and c["hops"] == 2
+    sim.close()
+    g.close()
+
+
+def test_random_small_graphs_property(dev, phys):
+    """Hypothesis-driven: arbitrary small multigraphs (parallel streets, self loops, several components,
+    integer / zero / continuous weights, shuffled device numbering): distances bit-equal, predecessors equal,
+    and a day's loads equal to the oracle's."""
+    from hypothesis import HealthCheck, given, settings as hsettings, strategies as st
+    from oracle import ctwin
+    from streets4mpi_b200 import engine
+
+    @st.composite
+    def cases(draw):
+        V = draw(st.integers(2, 28))
+        S = draw(st.integers(1, 70))
+        u = draw(st.lists(st.integers(0, V - 1), min_size=S, max_size=S))
+        v = draw(st.lists(st.integers(0, V - 1), min_size=S, max_size=S))
+        kind = draw(st.sampled_from(["int", "zero", "float"]))
+        if kind == "int":
+            w = [float(x) for x in draw(st.lists(st.integers(1, 3), min_size=S, max_size=S))]
+        elif kind == "zero":
+            w = [float(x) for x in draw(st.lists(st.integers(0, 2), min_size=S, max_size=S))]
+        else:
+            w = draw(st.lists(st.floats(0.01, 50.0, allow_nan=False), min_size=S, max_size=S))
+        perm = draw(st.permutations(list(range(V))))
+        ranked = draw(st.booleans())
+        src = draw(st.integers(0, V - 1))
+        trips = draw(st.lists(st.tuples(st.integers(0, V - 1), st.integers(0, V - 1)), min_size=1, max_size=30))
+        return V, u, v, w, (perm if ranked else None), src, trips
+
+    @hsettings(max_examples=60, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(cases())
+    def run(case):
+        V, u, v, w, perm, src, trips = case
+        u, v, w = np.array(u, np.int32), np.array(v, np.int32), np.array(w, np.float64)
+        S = len(u)
+        rank = None if perm is None else np.array(perm, np.int32)
+        g = engine.DeviceGraph(dev, V, u, v, np.full(S, 10.0), np.full(S, 50, np.int32), node_rank=rank)
+        csr = ctwin.Csr(V, u, v)
+        dist, pred = g.sssp(w, src)
+        d0, p0, _ = ctwin.sssp(csr, w, src)
+        assert np.array_equal(dist.view(np.uint64), d0.view(np.uint64))
+        assert np.array_equal(pred, p0)
+        g.close()
+        # a day on K1 weights (lengths double as the varying quantity so that K1 produces the ties / zeros)
+        length = np.where(w == 0.0, 0.0, w * 40.0)
+        g = engine.DeviceGraph(dev, V, u, v, length, np.full(S, 50, np.int32), node_rank=rank)
+        o = np.array([t[0] for t in trips], np.int32)
+        gl = np.array([t[1] for t in trips], np.int32)
+        sim = engine.DeviceSim(g, o, gl, 0.25, phys)
+        sim.step()
+        ww = ctwin.weights(length, np.full(S, 50, np.int32), np.zeros(S, np.uint32), 0.25)
+        want, cnt = ctwin.day(csr, ww, o, gl, nthreads=1)
+        c = sim.counters()
+        assert np.array_equal(sim.get_load(), want)
+        assert c["trips_unreachable"] == cnt["unreachable"] and c["trips_stuck"] == cnt["stuck"] and c["hops"] == cnt["hops"]
+        sim.close()
+        g.close()
+
+    old = dev.get_option("root_mode")
+    dev.set_option("root_mode", 0)
+    try:
+        run()
+    finally:
+        dev.set_option("root_mode", old)
