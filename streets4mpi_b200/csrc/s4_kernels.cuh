@@ -350,6 +350,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024
     __shared__ int s_root_idx;
     __shared__ u32 s_overflow;
     __shared__ u32 s_changed;
+    __shared__ u32 s_stat[3];           // bucket advances, relaxation rounds, fallback sweeps (thread 0 counts)
     __shared__ u32 s_bucket_rounds;     // relaxation rounds since the last bucket advance
     __shared__ u32 s_bucket_entries;    // entries popped in them
 
@@ -367,7 +368,8 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024
     double delta = p.delta_scale * (*p.wsum);
     if (!(delta > 0.0)) delta = 0.0;
 
-    u64 c_relax = 0, c_pop = 0, c_stale = 0, c_push = 0, c_adv = 0, c_round = 0, c_sweep = 0;
+    u64 c_relax = 0, c_pop = 0, c_stale = 0, c_push = 0;
+    if (tid == 0) { s_stat[0] = 0u; s_stat[1] = 0u; s_stat[2] = 0u; }
 
     for (;;) {
         __syncthreads();                       // previous tree fully retired before s_* are reused
@@ -401,7 +403,11 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024
         u32 c = 0;          // index of the current near counter
         u32 b = 0;          // current near buffer
         u32 f = 0;          // current far pile (push target)
-        u32 thr_hi = hi32((u64)__double_as_longlong(delta));   // near bucket = entries with hi32(d) <= thr_hi
+        u32 thr_hi;                                            // near bucket = entries with hi32(d) <= thr_hi
+        {
+            double delta = p.delta_scale * __ldg(p.wsum);
+            thr_hi = hi32((u64)__double_as_longlong(delta > 0.0 ? delta : 0.0));
+        }
 
         for (;;) {
             const u32 n = s_cnt[c];
@@ -412,13 +418,13 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024
                     s_cnt[cn == 2 ? 0 : cn + 1] = 0u;                  // counter of the round after next
                     s_bucket_rounds += 1u;
                     s_bucket_entries += n;
+                    s_stat[1] += 1u;
                 }
                 const Queue qc = near_q(b);
                 const Queue qn = near_q(b ^ 1u);
                 u32 *const fv = far_v(f);
                 u64 *const fd = far_d(f);
                 const u32 n_s = n < scap + gcap ? n : scap + gcap;      // entries that were actually stored
-                ++c_round;
                 for (u32 base = 0; base < n_s; base += BLOCK) {
                     const u32 i = base + tid;
                     bool valid = i < n_s;
@@ -472,7 +478,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024
             const u32 far_min_hi = s_far_min[f];
             // every thread must have seen s_cnt[c] == 0 before the split starts refilling that queue
             __syncthreads();
-            ++c_adv;
+            if (tid == 0) s_stat[0] += 1u;
             // new threshold: smallest (lower bound of a) distance in the pile + delta
             const double lo = __longlong_as_double((long long)((u64)far_min_hi << 32));
             // bucket width follows the wave: widen while the rounds of a bucket leave most of the CTA idle,
@@ -484,7 +490,11 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024
                     else if (be > br * (BLOCK * 4u) && dmul > 1.0) dmul *= (1.0 / 1.5);
                 }
             }
-            thr_hi = hi32((u64)__double_as_longlong(__dadd_rn(lo, delta * dmul)));
+            {
+                double delta = p.delta_scale * __ldg(p.wsum);
+                if (!(delta > 0.0)) delta = 0.0;
+                thr_hi = hi32((u64)__double_as_longlong(__dadd_rn(lo, delta * dmul)));
+            }
             const u32 fo = f ^ 1u;
             const u32 *srcv = far_v(f);
             const u64 *srcd = far_d(f);
@@ -516,9 +526,8 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024
         if (s_overflow) {
             for (;;) {
                 __syncthreads();
-                if (tid == 0) s_changed = 0u;
+                if (tid == 0) { s_changed = 0u; s_stat[2] += 1u; }
                 __syncthreads();
-                ++c_sweep;
                 bool any = false;
                 for (u32 u = tid; u < V; u += BLOCK) {
                     const u64 du = ld_dist(dist + u);
@@ -541,7 +550,8 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024
     }
 
     // ---- flush per-thread counters: one atomic per warp per counter
-    u64 vals[7] = {c_relax, c_pop, c_stale, c_push, tid == 0 ? c_adv : 0, tid == 0 ? c_round : 0, tid == 0 ? c_sweep : 0};
+    __syncthreads();
+    u64 vals[7] = {c_relax, c_pop, c_stale, c_push, tid == 0 ? s_stat[0] : 0u, tid == 0 ? s_stat[1] : 0u, tid == 0 ? s_stat[2] : 0u};
     const int ids[7] = {C_ARCS_RELAXED, C_NODES_POPPED, C_STALE_POPS, C_PUSHES, C_ADVANCES, C_ROUNDS, C_FALLBACK_SWEEPS};
 #pragma unroll
     for (int j = 0; j < 7; ++j) {
