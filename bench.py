@@ -420,6 +420,12 @@ def gpu_arm(args):
             "gteps": arcs_alg / (ms_max * 1e-3) / 1e9,
             "sssp_trees_per_sec": trees / (ms_max * 1e-3),
             "relaxations_per_algorithmic_arc": arcs_rel / max(1.0, arcs_alg),
+            # context: with the reference's own grouping (root_mode origin, one tree per distinct origin) the same
+            # kernels route this many trips/s -- estimate from the measured tree rate, not a separate run
+            "reference_grouping_estimate": {
+                "distinct_origins_rank0": int(np.unique(o).size),
+                "trips_per_sec": trees / (ms_max * 1e-3) * per_rank / max(1, int(np.unique(o).size)),
+                "note": "root_mode=origin needs one tree per distinct origin instead of per distinct goal"},
             "hops_per_trip": hops / max(1.0, trips),
             "kernel_ms_serial_day": {"weights": cs["ms_weights"], "sssp": cs["ms_sssp"], "walk": cs["ms_walk"],
                                      "sssp_share": cs["ms_sssp"] / serial_total if serial_total else None,
