@@ -94,14 +94,22 @@ const char *s4_last_error(void);
 int s4_ctx_create(int device, void *stream, s4_ctx **out);
 int s4_ctx_destroy(s4_ctx *ctx);
 int s4_ctx_sync(s4_ctx *ctx);
-/* Tunables (all have defaults): "delta_factor" (bucket width in mean arc
- * weights), "block_threads" (32|64|128|256|512|1024), "ctas_per_sm", "near_smem_entries", "queue_entries", "batch_roots",
- * "pool_bytes", "root_mode" (S4_ROOT_*), "walk_tile" (0 = auto|4|8|16|32),
- * "preread" (1 = filtering read then returning atomicMin, 2 = the filtering
- * read decides the push and the minimum goes out as a fire-and-forget
- * reduction), "lanes" (2 = a day's batches alternate between two concurrent
- * launch lanes, 1 = strictly serial kernels, e.g. for per-kernel timing),
- * "adaptive_delta" (1 = the bucket width follows the width of the wave). */
+/* Tunables; 0 means "chosen by the library" where noted.
+ *   "delta_factor"       near-bucket width in mean street weights (default 3)
+ *   "adaptive_delta"     1 (default): the width follows the wave (grows on thin waves, shrinks on floods)
+ *   "block_threads"      0 (default: from the graph's wave width) | 32 | 64 | 128 | 256 | 512 | 1024
+ *   "ctas_per_sm"        0 (default: 1024 threads per SM)
+ *   "near_smem_entries"  0 (default: 6 per thread) - shared-memory part of each near queue
+ *   "queue_entries"      0 (default: from V) - per-CTA spill / far-pile capacity
+ *   "pool_bytes"         bytes for the per-tree distance arrays (default 64e9, capped by free memory)
+ *   "batch_roots"        0 (default: from pool_bytes) - trees in flight
+ *   "root_mode"          S4_ROOT_* used by the next s4_sim_create
+ *   "walk_tile"          0 (default: 8) | 4 | 8 | 16 | 32 lanes per walking trip
+ *   "preread"            2 (default): the filtering read decides the push, the minimum goes out as a
+ *                        fire-and-forget reduction; 1: filtering read, then returning atomicMin
+ *   "lanes"              2 (default): a day's batches alternate between two concurrent launch lanes;
+ *                        1: strictly serial kernels (per-kernel timing)
+ * No option changes a result. */
 int s4_ctx_set_option(s4_ctx *ctx, const char *key, double value);
 int s4_ctx_get_option(s4_ctx *ctx, const char *key, double *value);
 /* name, SM count, bytes of HBM; name_out may be NULL */
