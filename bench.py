@@ -8,9 +8,11 @@ and GTEPS; sim-day time against the CPU reference path).
 A step is one simulated day: K1 weights -> K2 one shortest-path tree per root -> K3 walk of every
 trip -> exchange (NCCL all-reduce of the uint32 load + cumulative merge).  Workload (config.workload):
 BASELINE.json configs[2], the synthetic 1024x1024 grid (V=1,048,576 S=2,095,104 A=4,190,208), 1M
-trips/day per GPU (weak scaling: every GPU hosts one virtual rank with its own trip stream and jam
-tolerance, streets4mpi.py:50-51,69,78, and the ranks only meet in the daily all-reduce; --scaling strong
-divides one 1M-trip day over the GPUs instead), goals = seeded 2 % node sample.
+trips/day, goals = seeded 2 % node sample.  Default --scaling strong: ONE virtual rank (one trip list, one jam
+tolerance: the reference run without mpiexec) whose shortest-path trees, with the trips hanging off them, are
+dealt round-robin to the GPUs; the daily NCCL all-reduce sums the loads (bit-identical to the 1-GPU result).
+--scaling weak: one virtual rank with its own trips and jam tolerance per GPU (streets4mpi.py:50-51,69,78);
+--scaling ranks: the 1M trips divided over per-GPU virtual ranks, every rank needing its own trees.
 
 One JSON line on rank 0.  `value` = trips routed per second by the whole job with everything resident
 in HBM (CUDA events, max over ranks); `e2e` = the same through the reference-facing Python API with
@@ -51,10 +53,12 @@ def log(*a):
 # ----------------------------------------------------------------------------------------------
 # workload (identical for both arms)
 # ----------------------------------------------------------------------------------------------
-def make_workload(name, world, scaling="weak"):
+def make_workload(name, world, scaling="strong"):
     """scaling == "weak": every GPU (= one virtual rank with its own trip stream and jam tolerance) routes the
-    workload's full day, the job routes world x that; "strong": the day's trips are divided over the ranks
-    like streets4mpi.py:69 divides number_of_residents."""
+    workload's full day, the job routes world x that.  "strong": ONE virtual rank (one trip list, one jam
+    tolerance -- the reference started without mpiexec) whose shortest-path trees are dealt round-robin to the
+    GPUs (distributed.partition_by_root); the all-reduce sums the loads.  "ranks": the day's trips divided over
+    per-GPU virtual ranks like streets4mpi.py:69 divides number_of_residents (every rank needs its own trees)."""
     from streets4mpi_b200 import synth
     rows, cols, trips_total = WORKLOADS[name]
     if TRIPS_OVERRIDE:
@@ -63,7 +67,7 @@ def make_workload(name, world, scaling="weak"):
         trips_total *= world
     arrays = synth.grid_arrays(rows, cols, seed=1) if rows else synth.planar_arrays(cols, seed=1)
     cats = synth.node_categories(arrays["node_ids"], seed=1, goal_fraction=0.02)
-    per_rank = trips_total // world                       # streets4mpi.py:69
+    per_rank = trips_total if scaling == "strong" else trips_total // world      # streets4mpi.py:69
     return arrays, cats, per_rank
 
 
@@ -240,7 +244,8 @@ def reference_arm(args):
     line = {
         "impl": "reference", "metric": "routed_trips_per_sec", "value": value, "unit": "trips/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / max(1, args.steps),
-        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong" if args.scaling == "ranks" else args.scaling, "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload + ": " + workload_text(args.workload), "root_mode": "origin (reference grouping)",
                    "sample": sample},
         "cpu_baseline": {"value": value, "unit": "trips/s", "cores": cores, "kind": "port", "sample": sample},
@@ -278,9 +283,19 @@ def gpu_arm(args):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"        # keep NCCL's version banner off stdout: one JSON line only
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+        # NCCL prints its version banner on stdout when the first communicator is created; stdout must carry
+        # exactly one JSON line, so fd 1 points at stderr until the communicator exists
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize(local)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     import __graft_entry__ as ge
     if rank == 0:
@@ -301,7 +316,16 @@ def gpu_arm(args):
     settings["logging"] = None
 
     arrays, cats, per_rank = make_workload(args.workload, world, args.scaling)
-    o, g, jam = rank_trips(arrays, cats, per_rank, rank)
+    if args.scaling == "strong":
+        # one virtual rank for the whole job: rank 0's trip stream and jam tolerance, trees dealt to the GPUs
+        o, g, jam = rank_trips(arrays, cats, per_rank, 0)
+        o, g, forced = distributed.partition_by_root(o, g, rank, world, device_settings["root_mode"])
+        device_settings["root_mode"] = forced
+        job_trips = per_rank
+        per_rank = len(o)
+    else:
+        o, g, jam = rank_trips(arrays, cats, per_rank, rank)
+        job_trips = per_rank * world
     net = synth.network_from(arrays)
     t0 = time.perf_counter()
     sim = Simulation(net, TripTable(o, g), jam, lambda *a: None, device=dev)
@@ -406,13 +430,17 @@ def gpu_arm(args):
             threads = os.cpu_count() or 1
             v, desc, _ = cpu_sample(arrays, net.flat().dense(o), net.flat().dense(g), jam, args.cpu_seconds, threads)
             cpu = {"value": v, "unit": "trips/s", "cores": threads, "kind": "port", "sample": desc}
-        total_trips = per_rank * world * args.steps
+        total_trips = job_trips * args.steps
         line = {
             "metric": "routed_trips_per_sec", "value": total_trips / (ms_max * 1e-3), "unit": "trips/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
-            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong" if args.scaling == "ranks" else args.scaling,
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload + ": " + workload_text(args.workload),
-                       "trips_per_day": {"per_gpu": per_rank, "job": per_rank * world},
+                       "trips_per_day": {"per_gpu_rank0": per_rank, "job": job_trips},
+                       "decomposition": {"weak": "one virtual rank (own trips, own jam tolerance) per GPU",
+                                         "strong": "one virtual rank, its trees dealt round-robin to the GPUs",
+                                         "ranks": "the day's trips divided over per-GPU virtual ranks"}[args.scaling],
                        "root_mode": "%s (trees per day and GPU: %d)" % (mode, sim._sim.n_roots),
                        "virtual_ranks": world, "construction_every": args.construction_every,
                        "l2": "inputs larger than L2 (per-tree distance arrays, 8 B x V x trees in flight >> 126 MB)",
@@ -437,7 +465,7 @@ def gpu_arm(args):
                          "frac_overlapped_region": (20.0 * c["arcs_algorithmic"] + 20.0 * c["nodes_algorithmic"])
                          / (ms * 1e-3) / 1e9 / peak},
             "cpu_baseline": cpu,
-            "e2e": {"value": per_rank * world * e2e_steps / e2e_s, "unit": "trips/s", "steps": e2e_steps,
+            "e2e": {"value": job_trips * e2e_steps / e2e_s, "unit": "trips/s", "steps": e2e_steps,
                     "h2d_bytes_per_step": 8 * S, "d2h_bytes_per_step": 4 * S,
                     "api": "reference driver protocol (streets4mpi.py:93-100): Simulation.step(), array('I') "
                            "traffic_load read + assign, merge_arrays into cumulative_traffic_load; wall clock"},
@@ -465,8 +493,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-trees-per-core", type=int, default=1)
     ap.add_argument("--trips", type=int, default=0, help="override the workload's trips per day")
-    ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
-                    help="weak: the workload's day per GPU (one virtual rank each); strong: the day divided over the GPUs")
+    ap.add_argument("--scaling", choices=["weak", "strong", "ranks"], default="strong",
+                    help="weak: the workload's day per GPU (one virtual rank each); strong: one virtual rank, trees "
+                         "dealt to the GPUs; ranks: the day's trips divided over per-GPU virtual ranks")
     ap.add_argument("--construction-every", type=int, default=0, help="road adaptation every N days (0 = never)")
     args = ap.parse_args()
     global TRIPS_OVERRIDE

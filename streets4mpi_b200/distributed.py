@@ -38,6 +38,24 @@ def residents_of_rank(number_of_residents, world_size):
     return number_of_residents // world_size
 
 
+def partition_by_root(origins, goals, rank, world_size, root_mode=2):
+    """Tree-parallel decomposition of ONE virtual rank (one trip list, one jam tolerance) over several GPUs.
+
+    The reference's only parallel axis is "ranks own trips" and every rank owns its jam tolerance, hence its own
+    weights and trees (streets4mpi.py:69,78).  A single rank's day is however a sum over independent
+    shortest-path trees, so its trees -- with the trips hanging off them -- can be dealt round-robin to the
+    GPUs; the uint32 loads are summed by the same all-reduce and equal the single-process result bit for bit.
+    Returns (origins, goals, forced_root_mode) of this GPU's share; root_mode as in include/s4mpi.h
+    (2 = whichever endpoint set has fewer distinct nodes, decided on the whole list)."""
+    origins, goals = np.asarray(origins), np.asarray(goals)
+    if root_mode == 2:
+        root_mode = 1 if len(np.unique(goals)) < len(np.unique(origins)) else 0
+    roots = goals if root_mode == 1 else origins
+    _, index = np.unique(roots, return_inverse=True)          # rank of every trip's root among the distinct roots
+    mine = (index % world_size) == rank
+    return origins[mine], goals[mine], root_mode
+
+
 def allreduce_u32_(tensor, group=None):
     """In-place SUM all-reduce of a uint32 buffer held as an int32 torch tensor
     (CPU tensor + gloo in the tests, CUDA tensor + NCCL on the GPUs)."""

@@ -66,3 +66,23 @@ def test_single_process_is_identity():
     assert list(distributed.allreduce_array_I(array("I", a.tolist()))) == a.tolist()
     with pytest.raises(TypeError):
         distributed.allreduce_u32_(torch.zeros(3))
+
+
+def test_partition_by_root_is_an_exact_cover():
+    """Tree-parallel decomposition of one virtual rank: every trip lands on exactly one GPU, no tree is split,
+    the tree counts are balanced, and the forced root mode is the globally smaller endpoint set."""
+    from streets4mpi_b200 import distributed
+    rng = np.random.default_rng(3)
+    o = rng.integers(0, 5000, 20000)
+    g = rng.choice(np.arange(0, 5000, 50), 20000)               # 100 distinct goals
+    for world in (1, 2, 3, 8):
+        parts = [distributed.partition_by_root(o, g, r, world, 2) for r in range(world)]
+        assert all(p[2] == 1 for p in parts)                     # goal-rooted: 100 goals < ~4900 origins
+        assert sum(len(p[0]) for p in parts) == len(o)
+        roots = [set(np.unique(p[1]).tolist()) for p in parts]
+        assert sum(len(r) for r in roots) == 100 and len(set().union(*roots)) == 100
+        assert max(len(r) for r in roots) - min(len(r) for r in roots) <= 1
+        merged = np.sort(np.concatenate([p[0] * 10000 + p[1] for p in parts]))
+        assert np.array_equal(merged, np.sort(o * 10000 + g))
+    assert distributed.partition_by_root(g, o, 0, 2, 2)[2] == 0   # fewer distinct origins -> origin-rooted
+    assert distributed.partition_by_root(o, g, 0, 2, 0)[2] == 0   # explicit mode is respected
