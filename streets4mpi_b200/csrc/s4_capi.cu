@@ -62,6 +62,10 @@ struct Options {
     int walk_tile = 0;              // lanes per walking trip; 0 = from the graph's degrees
     int lanes = 2;                  // concurrent (SSSP launch -> walk) lanes per day; 1 = strictly serial kernels
     int adaptive_delta = 1;         // widen / narrow the bucket with the wave
+    int sssp_variant = 0;           // 0: CTA-wide relaxation rounds (one barrier per round);
+                                    // 2: warp-autonomous buckets (per-warp rings, two barriers per bucket)
+    int arc_unroll = 0;             // 0: one thread expands one frontier entry (all four ELL slots);
+                                    // 1 / 2 / 4: four lanes per entry (one slot each), that many entries per thread in flight
     int preread = 2;                // 1: filtering read, then returning atomicMin;
                                     // 2: filtering read decides the push, minimum sent as RED (no wait)
 };
@@ -256,7 +260,8 @@ static void option_slot(Options &o, const char *key, int *kind, void **raw)
         {"batch_roots", 2, &o.batch_roots},         {"pool_bytes", 0, &o.pool_bytes},
         {"root_mode", 1, &o.root_mode},             {"walk_tile", 1, &o.walk_tile},
         {"preread", 1, &o.preread},                 {"lanes", 1, &o.lanes},
-        {"adaptive_delta", 1, &o.adaptive_delta},
+        {"adaptive_delta", 1, &o.adaptive_delta},   {"arc_unroll", 1, &o.arc_unroll},
+        {"sssp_variant", 1, &o.sssp_variant},
     };
     for (auto &it : items)
         if (strcmp(it.k, key) == 0) { *kind = it.kind; *raw = it.p; return; }
@@ -282,7 +287,9 @@ extern "C" int s4_ctx_set_option(s4_ctx *ctx, const char *key, double value)
               (t.near_smem_entries == 0 || (t.near_smem_entries >= 32 && t.near_smem_entries <= 9000)) && t.queue_entries >= 0 &&
               t.batch_roots >= 0 && t.pool_bytes >= 0.0 && t.root_mode >= 0 && t.root_mode <= 2 &&
               (t.walk_tile == 0 || t.walk_tile == 4 || t.walk_tile == 8 || t.walk_tile == 16 || t.walk_tile == 32) &&
-              (t.preread == 1 || t.preread == 2) && (t.lanes == 1 || t.lanes == 2);
+              (t.preread == 1 || t.preread == 2) && (t.lanes == 1 || t.lanes == 2) &&
+              (t.arc_unroll == 0 || t.arc_unroll == 1 || t.arc_unroll == 2 || t.arc_unroll == 4) &&
+              (t.sssp_variant == 0 || t.sssp_variant == 2);
     if (!ok) return fail(S4_ERR_ARG, "option '%s': value %g out of range", key, value);
     ctx->opt = trial;
     return S4_OK;
@@ -515,16 +522,34 @@ extern "C" int s4_graph_dims(s4_graph *g, int32_t *V, int64_t *S, int64_t *A)
 // ---------------------------------------------------------------------------
 typedef void (*SsspKernel)(SsspParams);
 
-static SsspKernel pick_sssp(int block)
+static SsspKernel pick_sssp(int block, int unroll, int variant)
 {
-    switch (block) {
-        case 32: return sssp_nearfar_kernel<32>;
-        case 64: return sssp_nearfar_kernel<64>;
-        case 128: return sssp_nearfar_kernel<128>;
-        case 256: return sssp_nearfar_kernel<256>;
-        case 512: return sssp_nearfar_kernel<512>;
-        case 1024: return sssp_nearfar_kernel<1024>;
+    if (variant == 2) {
+        switch (block) {
+            case 32: return sssp_warpq_kernel<32>;
+            case 64: return sssp_warpq_kernel<64>;
+            case 128: return sssp_warpq_kernel<128>;
+            case 256: return sssp_warpq_kernel<256>;
+            case 512: return sssp_warpq_kernel<512>;
+            case 1024: return sssp_warpq_kernel<1024>;
+        }
+        return nullptr;
     }
+#define S4_PICK(B)                                               \
+    case B:                                                      \
+        return unroll == 0 ? sssp_nearfar_kernel<B, 0>           \
+               : unroll == 1 ? sssp_nearfar_kernel<B, 1>         \
+               : unroll == 2 ? sssp_nearfar_kernel<B, 2>         \
+                             : sssp_nearfar_kernel<B, 4>;
+    switch (block) {
+        S4_PICK(32)
+        S4_PICK(64)
+        S4_PICK(128)
+        S4_PICK(256)
+        S4_PICK(512)
+        S4_PICK(1024)
+    }
+#undef S4_PICK
     return nullptr;
 }
 
@@ -552,11 +577,19 @@ static int plan_sssp(s4_graph *g, SsspLaunch *L)
     }
     const int near_entries = o.near_smem_entries ? o.near_smem_entries : std::max(128, 6 * block);     // measured on cfg3
     const int ctas = o.ctas_per_sm ? o.ctas_per_sm : std::min(32, std::max(1, 1024 / block));
-    L->fn = pick_sssp(block);
+    L->fn = pick_sssp(block, o.arc_unroll, o.sssp_variant);
     if (!L->fn) return fail(S4_ERR_ARG, "no SSSP kernel for block=%d", block);
     L->block = block;
-    L->scap = (u32)near_entries;
-    L->smem = (size_t)2 * L->scap * (sizeof(u64) + sizeof(u32));
+    if (o.sssp_variant == 2) {
+        // one ring per warp, power-of-two entries (default 256: a pass pops 32 and pushes at most 128)
+        u32 ring = 256;
+        if (o.near_smem_entries) { ring = 32; while (ring * 2 <= (u32)o.near_smem_entries && ring < 4096) ring *= 2; }
+        L->scap = ring;
+        L->smem = (size_t)(block / 32) * ring * (sizeof(u64) + sizeof(u32));
+    } else {
+        L->scap = (u32)near_entries;
+        L->smem = (size_t)2 * L->scap * (sizeof(u64) + sizeof(u32));
+    }
     CU(cudaFuncSetAttribute((const void *)L->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L->smem));
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)L->fn, L->block, L->smem));

@@ -28,6 +28,10 @@ class Device(object):
         check(self.lib.s4_ctx_create(self.index, C.c_void_p(stream) if stream else None, C.byref(h)))
         self._h = h
         self.stream = int(stream) if stream else None      # None: library-owned stream
+        # tuning hook for A/B runs of the kernels: S4MPI_OPTIONS="key=value,key=value" (see s4_ctx_set_option)
+        for item in filter(None, os.environ.get("S4MPI_OPTIONS", "").split(",")):
+            key, _, value = item.partition("=")
+            self.set_option(key.strip(), float(value))
 
     def close(self):
         if getattr(self, "_h", None):
