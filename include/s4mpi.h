@@ -107,10 +107,9 @@ int s4_ctx_sync(s4_ctx *ctx);
  *   "walk_tile"          0 (default: 8) | 4 | 8 | 16 | 32 lanes per walking trip
  *   "preread"            2 (default): the filtering read decides the push, the minimum goes out as a
  *                        fire-and-forget reduction; 1: filtering read, then returning atomicMin
- *   "sssp_variant"       0 (default): CTA-wide relaxation rounds; 2: warp-autonomous buckets (per-warp rings in
- *                        shared memory, two CTA barriers per bucket instead of one per round)
- *   "arc_unroll"         0 (default): one thread expands a frontier entry (four ELL slots); 1 | 2 | 4: four lanes
- *                        per entry, that many entries per thread in flight (sssp_variant 0 only)
+ *   "early_advance"      2 (default): the next bucket is admitted as soon as a relaxation round (not one of the first
+ *                        two of its bucket) holds fewer entries than 2/8 of a CTA - the thinning tail of a bucket
+ *                        overlaps the head of the next; 0: only when the near queue is empty
  *   "lanes"              2 (default): a day's batches alternate between two concurrent launch lanes;
  *                        1: strictly serial kernels (per-kernel timing)
  * No option changes a result. */

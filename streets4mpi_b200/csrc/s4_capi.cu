@@ -62,10 +62,8 @@ struct Options {
     int walk_tile = 0;              // lanes per walking trip; 0 = from the graph's degrees
     int lanes = 2;                  // concurrent (SSSP launch -> walk) lanes per day; 1 = strictly serial kernels
     int adaptive_delta = 1;         // widen / narrow the bucket with the wave
-    int sssp_variant = 0;           // 0: CTA-wide relaxation rounds (one barrier per round);
-                                    // 2: warp-autonomous buckets (per-warp rings, two barriers per bucket)
-    int arc_unroll = 0;             // 0: one thread expands one frontier entry (all four ELL slots);
-                                    // 1 / 2 / 4: four lanes per entry (one slot each), that many entries per thread in flight
+    int early_advance = 2;          // admit the next bucket when a round has fewer entries than this many eighths of a CTA
+                                    // (0 = only when the near queue is empty); measured on cfg3 and a planar graph
     int preread = 2;                // 1: filtering read, then returning atomicMin;
                                     // 2: filtering read decides the push, minimum sent as RED (no wait)
 };
@@ -260,8 +258,7 @@ static void option_slot(Options &o, const char *key, int *kind, void **raw)
         {"batch_roots", 2, &o.batch_roots},         {"pool_bytes", 0, &o.pool_bytes},
         {"root_mode", 1, &o.root_mode},             {"walk_tile", 1, &o.walk_tile},
         {"preread", 1, &o.preread},                 {"lanes", 1, &o.lanes},
-        {"adaptive_delta", 1, &o.adaptive_delta},   {"arc_unroll", 1, &o.arc_unroll},
-        {"sssp_variant", 1, &o.sssp_variant},
+        {"adaptive_delta", 1, &o.adaptive_delta},   {"early_advance", 1, &o.early_advance},
     };
     for (auto &it : items)
         if (strcmp(it.k, key) == 0) { *kind = it.kind; *raw = it.p; return; }
@@ -288,8 +285,7 @@ extern "C" int s4_ctx_set_option(s4_ctx *ctx, const char *key, double value)
               t.batch_roots >= 0 && t.pool_bytes >= 0.0 && t.root_mode >= 0 && t.root_mode <= 2 &&
               (t.walk_tile == 0 || t.walk_tile == 4 || t.walk_tile == 8 || t.walk_tile == 16 || t.walk_tile == 32) &&
               (t.preread == 1 || t.preread == 2) && (t.lanes == 1 || t.lanes == 2) &&
-              (t.arc_unroll == 0 || t.arc_unroll == 1 || t.arc_unroll == 2 || t.arc_unroll == 4) &&
-              (t.sssp_variant == 0 || t.sssp_variant == 2);
+              t.early_advance >= 0 && t.early_advance <= 64;
     if (!ok) return fail(S4_ERR_ARG, "option '%s': value %g out of range", key, value);
     ctx->opt = trial;
     return S4_OK;
@@ -522,34 +518,16 @@ extern "C" int s4_graph_dims(s4_graph *g, int32_t *V, int64_t *S, int64_t *A)
 // ---------------------------------------------------------------------------
 typedef void (*SsspKernel)(SsspParams);
 
-static SsspKernel pick_sssp(int block, int unroll, int variant)
+static SsspKernel pick_sssp(int block)
 {
-    if (variant == 2) {
-        switch (block) {
-            case 32: return sssp_warpq_kernel<32>;
-            case 64: return sssp_warpq_kernel<64>;
-            case 128: return sssp_warpq_kernel<128>;
-            case 256: return sssp_warpq_kernel<256>;
-            case 512: return sssp_warpq_kernel<512>;
-            case 1024: return sssp_warpq_kernel<1024>;
-        }
-        return nullptr;
-    }
-#define S4_PICK(B)                                               \
-    case B:                                                      \
-        return unroll == 0 ? sssp_nearfar_kernel<B, 0>           \
-               : unroll == 1 ? sssp_nearfar_kernel<B, 1>         \
-               : unroll == 2 ? sssp_nearfar_kernel<B, 2>         \
-                             : sssp_nearfar_kernel<B, 4>;
     switch (block) {
-        S4_PICK(32)
-        S4_PICK(64)
-        S4_PICK(128)
-        S4_PICK(256)
-        S4_PICK(512)
-        S4_PICK(1024)
+        case 32: return sssp_nearfar_kernel<32>;
+        case 64: return sssp_nearfar_kernel<64>;
+        case 128: return sssp_nearfar_kernel<128>;
+        case 256: return sssp_nearfar_kernel<256>;
+        case 512: return sssp_nearfar_kernel<512>;
+        case 1024: return sssp_nearfar_kernel<1024>;
     }
-#undef S4_PICK
     return nullptr;
 }
 
@@ -577,19 +555,11 @@ static int plan_sssp(s4_graph *g, SsspLaunch *L)
     }
     const int near_entries = o.near_smem_entries ? o.near_smem_entries : std::max(128, 6 * block);     // measured on cfg3
     const int ctas = o.ctas_per_sm ? o.ctas_per_sm : std::min(32, std::max(1, 1024 / block));
-    L->fn = pick_sssp(block, o.arc_unroll, o.sssp_variant);
+    L->fn = pick_sssp(block);
     if (!L->fn) return fail(S4_ERR_ARG, "no SSSP kernel for block=%d", block);
     L->block = block;
-    if (o.sssp_variant == 2) {
-        // one ring per warp, power-of-two entries (default 256: a pass pops 32 and pushes at most 128)
-        u32 ring = 256;
-        if (o.near_smem_entries) { ring = 32; while (ring * 2 <= (u32)o.near_smem_entries && ring < 4096) ring *= 2; }
-        L->scap = ring;
-        L->smem = (size_t)(block / 32) * ring * (sizeof(u64) + sizeof(u32));
-    } else {
-        L->scap = (u32)near_entries;
-        L->smem = (size_t)2 * L->scap * (sizeof(u64) + sizeof(u32));
-    }
+    L->scap = (u32)near_entries;
+    L->smem = (size_t)2 * L->scap * (sizeof(u64) + sizeof(u32));
     CU(cudaFuncSetAttribute((const void *)L->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L->smem));
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)L->fn, L->block, L->smem));
@@ -652,6 +622,7 @@ static int launch_sssp(s4_graph *g, const SsspLaunch &L, const Arc *ell, const A
     p.far_cap = g->far_cap;
     p.preread = (u32)g->ctx->opt.preread;
     p.adaptive = (u32)g->ctx->opt.adaptive_delta;
+    p.early_advance = (u32)(g->ctx->opt.early_advance * L.block / 8);
     p.counters = counters;
     const int grid = std::min(L.grid, std::max(1, n_roots));
     L.fn<<<grid, L.block, L.smem, st>>>(p);

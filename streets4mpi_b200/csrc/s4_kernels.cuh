@@ -202,6 +202,7 @@ struct SsspParams {
     u32 far_cap;            // entries per far pile
     u32 preread;            // 1: filtering read, then returning atomicMin; 2: filtering read decides the push, RED.MIN
     u32 adaptive;           // 1: the bucket width follows the width of the wave
+    u32 early_advance;      // admit the next bucket as soon as a round (not the first two of its bucket) has fewer entries
     u64 *counters;
 };
 
@@ -280,24 +281,24 @@ __device__ __forceinline__ bool expand_entry(const Arc *__restrict__ ell, u64 *d
     return true;
 }
 
-struct Queue {
-    u32 *sv; u64 *sd;       // shared-memory part (scap entries)
-    u32 *gv; u64 *gd;       // global spill (gcap entries)
+// Where a round's pushes go (CTA-uniform).  The shared-memory part of the next near queue is addressed directly;
+// its global spill and the far pile are 32-bit offsets into the CTA's workspace (SoA: entry words / distances),
+// so a store costs one select and one scaled add instead of a re-derived 64-bit pointer per home.
+struct PushTarget {
+    u32 *sv; u64 *sd;       // next near queue, shared-memory part (scap entries)
+    u32 *wv; u64 *wd;       // this CTA's workspace
+    u32 near_off;           // workspace offset of that queue's spill, minus scap (entry idx >= scap lives at near_off + idx)
+    u32 far_off;            // workspace offset of the far pile
+    u32 scap, near_lim;     // near_lim = scap + spill capacity
+    u32 fcap;
 };
-
-__device__ __forceinline__ void q_store(const Queue &q, u32 scap, u32 gcap, u32 idx, u32 v, u64 d, u32 *overflow)
-{
-    if (idx < scap) { q.sv[idx] = v; q.sd[idx] = d; }
-    else if (idx - scap < gcap) { q.gv[idx - scap] = v; q.gd[idx - scap] = d; }
-    else *overflow = 1u;
-}
 
 // Warp-cooperative append of up to N candidates per lane: kind[j] 1 = near queue, 2 = far pile.
 // One scan over packed (near, far) counts, one shared-memory atomic per queue per warp.
 template <int N>
 __device__ __forceinline__ void warp_push(const u32 (&kind)[N], const u32 (&pv)[N], const u64 (&pd)[N], u32 lane,
-                                          const Queue &nq, u32 *near_cnt, u32 scap, u32 gcap, u32 *far_v, u64 *far_d,
-                                          u32 *far_cnt, u32 *far_min, u32 fcap, u32 *overflow, u64 &c_push)
+                                          const PushTarget &t, u32 *near_cnt, u32 *far_cnt, u32 *far_min, u32 *overflow,
+                                          u64 &c_push)
 {
     u32 packed = 0, mymin = 0xFFFFFFFFu;
 #pragma unroll
@@ -308,8 +309,8 @@ __device__ __forceinline__ void warp_push(const u32 (&kind)[N], const u32 (&pv)[
     u32 incl = packed;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
-        if ((int)lane >= o) incl += t;
+        const u32 t_ = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane >= o) incl += t_;
     }
     const u32 total = __shfl_sync(0xffffffffu, incl, 31);
     if (total == 0u) return;                                   // warp-uniform
@@ -325,69 +326,23 @@ __device__ __forceinline__ void warp_push(const u32 (&kind)[N], const u32 (&pv)[
     u32 on = base_n + (excl & 0xFFFFu), of = base_f + (excl >> 16);
 #pragma unroll
     for (int j = 0; j < N; ++j) {
-        if (kind[j] == 1u) q_store(nq, scap, gcap, on++, pv[j], pd[j], overflow);
-        else if (kind[j] == 2u) {
-            if (of < fcap) { far_v[of] = pv[j]; far_d[of] = pd[j]; } else *overflow = 1u;
-            ++of;
+        if (kind[j]) {
+            const bool is_near = kind[j] == 1u;
+            const u32 idx = is_near ? on : of;
+            on += is_near ? 1u : 0u;
+            of += is_near ? 0u : 1u;
+            if (is_near && idx < t.scap) { t.sv[idx] = pv[j]; t.sd[idx] = pd[j]; }
+            else if (idx < (is_near ? t.near_lim : t.fcap)) {
+                const u32 off = (is_near ? t.near_off : t.far_off) + idx;
+                t.wv[off] = pv[j];
+                t.wd[off] = pd[j];
+            } else *overflow = 1u;
         }
     }
     c_push += (packed & 0xFFFFu) + (packed >> 16);
 }
 
-
-// ---------------------------------------------------------------------------
-// Arc-parallel expansion (template parameter UN > 0 of the kernel below): four lanes share one
-// frontier entry, lane j owning ELL slot j.  Per entry the warp issues ONE 64-byte row request
-// (four 16-byte lanes) and ONE 32-byte request for the sector of dist[] that holds the node (lane j
-// reads word j); the entry's own distance and every neighbour inside that sector travel by shuffle.
-// The code is branch-free up to the stores: pushes are placed with two ballots (near / far) per
-// unrolled entry and one shared-memory atomic per queue and warp.  UN entries per thread are in
-// flight together (memory-level parallelism of the thread-per-node variant at a fraction of its
-// instruction count: no 4x unrolled divergent relax / store code, no warp scan).
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ u64 shfl64(u64 x, u32 src)
-{
-    const u32 lo = __shfl_sync(0xffffffffu, (u32)x, (int)src);
-    const u32 hi = __shfl_sync(0xffffffffu, (u32)(x >> 32), (int)src);
-    return ((u64)hi << 32) | lo;
-}
-
-// Ballot-placed append of at most one candidate per lane (kind 1 = near queue, 2 = far pile).  In the
-// arc-parallel variant the near queues live in shared memory only: an entry that does not fit goes to
-// the far pile instead (it is then below the threshold of the next bucket advance and simply comes back
-// one advance later -- the order of expansion never affects the fixed point).
-__device__ __forceinline__ void warp_push1(u32 kind, u32 v, u64 d, u32 lane, u32 *nsv, u64 *nsd, u32 *near_cnt, u32 scap,
-                                           u32 *far_v, u64 *far_d, u32 *far_cnt, u32 *far_min, u32 fcap, u32 *overflow,
-                                           u32 &c_push)
-{
-    const u32 mn = __ballot_sync(0xffffffffu, kind == 1u);
-    bool to_far = kind == 2u;
-    if ((mn | __ballot_sync(0xffffffffu, to_far)) == 0u) return;    // warp-uniform
-    const u32 lt = (1u << lane) - 1u;
-    if (mn) {
-        u32 bn = 0;
-        if (lane == 0) bn = atomicAdd(near_cnt, (u32)__popc(mn));
-        bn = __shfl_sync(0xffffffffu, bn, 0);
-        if (kind == 1u) {
-            const u32 idx = bn + (u32)__popc(mn & lt);
-            if (idx < scap) { nsv[idx] = v; nsd[idx] = d; } else to_far = true;
-        }
-    }
-    const u32 mf = __ballot_sync(0xffffffffu, to_far);
-    if (mf) {
-        const u32 wmin = __reduce_min_sync(0xffffffffu, to_far ? hi32(d) : 0xFFFFFFFFu);
-        u32 bf = 0;
-        if (lane == 0) { bf = atomicAdd(far_cnt, (u32)__popc(mf)); atomicMin(far_min, wmin); }
-        bf = __shfl_sync(0xffffffffu, bf, 0);
-        if (to_far) {
-            const u32 idx = bf + (u32)__popc(mf & lt);
-            if (idx < fcap) { far_v[idx] = v; far_d[idx] = d; } else *overflow = 1u;
-        }
-    }
-    c_push += kind != 0u ? 1u : 0u;
-}
-
-template <int BLOCK, int UN>
+template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024 / BLOCK : 1)) sssp_nearfar_kernel(SsspParams p)
 {
     static_assert(BLOCK % 32 == 0, "whole warps");
@@ -414,9 +369,10 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024
     u32 *wv = p.ws_v + (size_t)blockIdx.x * ws_stride;
     u64 *wd = p.ws_d + (size_t)blockIdx.x * ws_stride;
     // queue b / far pile f by arithmetic (no dynamically indexed local arrays)
-    auto near_q = [&](u32 b_) { return Queue{sv0 + b_ * scap, sd0 + b_ * scap, wv + (size_t)b_ * gcap, wd + (size_t)b_ * gcap}; };
-    auto far_v = [&](u32 f_) { return wv + 2 * (size_t)gcap + (size_t)f_ * fcap; };
-    auto far_d = [&](u32 f_) { return wd + 2 * (size_t)gcap + (size_t)f_ * fcap; };
+    // pushes of a round go to near queue nb (shared part + spill) and far pile nf_ (32-bit workspace offsets)
+    auto target = [&](u32 nb, u32 nf_) {
+        return PushTarget{sv0 + nb * scap, sd0 + nb * scap, wv, wd, nb * gcap - scap, 2u * gcap + nf_ * fcap, scap, scap + gcap, fcap};
+    };
 
     double delta = p.delta_scale * (*p.wsum);
     if (!(delta > 0.0)) delta = 0.0;
@@ -452,7 +408,6 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024
         if (tid == 0) dist[root] = 0ull;                   // after the fill
         __syncthreads();
 
-        u32 t_pop = 0, t_stale = 0, t_push = 0, t_xarcs = 0;   // arc-parallel variant: per-tree counts, folded below
         double dmul = 1.0;  // adaptive multiplier of the bucket width
         u32 c = 0;          // index of the current near counter
         u32 b = 0;          // current near buffer
@@ -463,9 +418,19 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024
             thr_hi = hi32((u64)__double_as_longlong(delta > 0.0 ? delta : 0.0));
         }
 
+        u32 rib = 0;                // rounds in the current bucket
+        bool force_round = false;   // an early advance found the far pile empty: run the round instead
         for (;;) {
             const u32 n = s_cnt[c];
-            if (n > 0) {
+            // Overlapped buckets: the last rounds of a bucket are a thinning cascade that leaves most of the CTA idle.
+            // Once a round is that small, the next bucket is admitted on top of it (the split appends to the queue the
+            // round would have read).  The threshold still moves one bucket width per advance, so there are no more
+            // split passes than before, only fewer near-empty rounds.
+            // (n, rib and force_round are CTA-uniform: s_cnt[c] is not written during the round that follows.)
+            const bool early = n > 0u && n < p.early_advance && rib >= 2u && !force_round;
+            if (n > 0 && !early) {
+                ++rib;
+                force_round = false;
                 // ------------------------- relaxation round -------------------------
                 const u32 cn = c == 2 ? 0 : c + 1;
                 if (tid == 0) {
@@ -474,140 +439,11 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024
                     s_bucket_entries += n;
                     s_stat[1] += 1u;
                 }
-                const Queue qc = near_q(b);
-                const Queue qn = near_q(b ^ 1u);
-                u32 *const fv = far_v(f);
-                u64 *const fd = far_d(f);
+                const u32 *const csv = sv0 + b * scap;                      // the queue this round reads
+                const u64 *const csd = sd0 + b * scap;
+                const u32 cur_off = b * gcap - scap;                        // its spill: entry i >= scap at cur_off + i
+                const PushTarget tg = target(b ^ 1u, f);
                 const u32 n_s = n < scap + gcap ? n : scap + gcap;      // entries that were actually stored
-                (void)n_s;
-                if constexpr (UN > 0) {
-                    // ---- arc-parallel: four lanes per entry, UN entries per thread in flight; the near
-                    // queues are shared memory only (n_s <= scap)
-                    constexpr u32 EPP = BLOCK / 4;                      // entries per sub-pass of the CTA
-                    const u32 grp = tid >> 2, j = tid & 3u, gl = lane & ~3u;
-                    const u32 lt = (1u << lane) - 1u;
-                    const u32 *const csv = sv0 + b * scap;
-                    const u64 *const csd = sd0 + b * scap;
-                    u32 *const nsv = sv0 + (b ^ 1u) * scap;
-                    u64 *const nsd = sd0 + (b ^ 1u) * scap;
-                    u32 *const ncnt = &s_cnt[cn];
-                    const u32 n_q = n < scap ? n : scap;
-                    for (u32 base = 0; base < n_q; base += EPP * UN) {
-                        u32 ent[UN], word[UN];
-                        u64 du[UN], secw[UN], pdv[UN], old[UN];
-                        double aw[UN];
-                        bool val[UN], cand[UN], ovf[UN];
-                        // phase 1: entry (shared memory), ELL slot j and word j of the node's distance sector
-#pragma unroll
-                        for (int k = 0; k < UN; ++k) {
-                            const u32 i = base + (u32)k * EPP + grp;
-                            val[k] = i < n_q;
-                            ent[k] = 0u; du[k] = 0ull; secw[k] = 0ull; word[k] = 0u; aw[k] = 0.0; ovf[k] = false;
-                            if (val[k]) {
-                                ent[k] = csv[i];
-                                du[k] = csd[i];
-                                const u32 u = ent[k] & kNodeMask;
-                                const Arc a = ld_arc(p.ell + (size_t)u * kEllWidth + j);
-                                secw[k] = ld_dist(dist + (u & ~3u) + j);
-                                word[k] = a.street;                             // entry word of the head (node | reverse slot)
-                                aw[k] = a.w;
-                                ovf[k] = (a.col & kOvfBit) != 0u;               // only slot 0 carries the flag
-                            }
-                        }
-                        // phase 2: stale check, candidate distance, filtering read of dist[head]
-#pragma unroll
-                        for (int k = 0; k < UN; ++k) {
-                            const u32 u = ent[k] & kNodeMask, skip = ent[k] >> 28;
-                            const u32 head = word[k] & kNodeMask;
-                            const u64 own = shfl64(secw[k], gl + (u & 3u));
-                            const u64 nbs = shfl64(secw[k], gl + (head & 3u));
-                            const bool live = val[k] && !(own < du[k]);             // else superseded by a later push
-                            pdv[k] = (u64)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)du[k]), aw[k]));
-                            cand[k] = live && j != skip && pdv[k] < kInfBits;        // padding slots have w == +inf
-                            const bool insec = (head >> 2) == (u >> 2);
-                            old[k] = insec ? nbs : kInfBits;
-                            if (cand[k] && !insec) old[k] = ld_dist(dist + head);
-                            ovf[k] = ovf[k] && live && j == 0u;
-                            if (j == 0u) { t_pop += live ? 1u : 0u; t_stale += (val[k] && !live) ? 1u : 0u; }
-                        }
-                        // phase 3: fire-and-forget minimum, classification, ballot-placed pushes
-                        u32 mn[UN], mf[UN], tn = 0, tf = 0, myfar = 0xFFFFFFFFu;
-#pragma unroll
-                        for (int k = 0; k < UN; ++k) {
-                            const bool imp = cand[k] && pdv[k] < old[k];
-                            if (imp) atomicMin(dist + (word[k] & kNodeMask), pdv[k]);
-                            const bool nr = imp && hi32(pdv[k]) <= thr_hi;
-                            const bool fr = imp && !nr;
-                            cand[k] = nr;                                            // reuse: near flag
-                            val[k] = fr;                                             //        far flag
-                            mn[k] = __ballot_sync(0xffffffffu, nr);
-                            mf[k] = __ballot_sync(0xffffffffu, fr);
-                            tn += (u32)__popc(mn[k]);
-                            tf += (u32)__popc(mf[k]);
-                            if (fr) myfar = min(myfar, hi32(pdv[k]));
-                            t_push += imp ? 1u : 0u;
-                        }
-                        if (tn | tf) {                                               // warp-uniform
-                            u32 bn = 0, bf = 0;
-                            if (tf) {
-                                const u32 wmin = __reduce_min_sync(0xffffffffu, myfar);
-                                if (lane == 0) { bf = atomicAdd(&s_far_cnt[f], tf); atomicMin(&s_far_min[f], wmin); }
-                            }
-                            if (tn && lane == 0) bn = atomicAdd(ncnt, tn);
-                            bn = __shfl_sync(0xffffffffu, bn, 0);
-                            bf = __shfl_sync(0xffffffffu, bf, 0);
-                            const bool spills = bn + tn > scap;                      // warp-uniform, rare
-#pragma unroll
-                            for (int k = 0; k < UN; ++k) {
-                                if (cand[k]) {
-                                    const u32 idx = bn + (u32)__popc(mn[k] & lt);
-                                    if (idx < scap) { nsv[idx] = word[k]; nsd[idx] = pdv[k]; cand[k] = false; }
-                                }
-                                if (val[k]) {
-                                    const u32 idx = bf + (u32)__popc(mf[k] & lt);
-                                    if (idx < fcap) { fv[idx] = word[k]; fd[idx] = pdv[k]; } else s_overflow = 1u;
-                                }
-                                bn += (u32)__popc(mn[k]);
-                                bf += (u32)__popc(mf[k]);
-                            }
-                            if (spills) {
-                                // near entries that found the shared-memory queue full go to the far pile
-#pragma unroll
-                                for (int k = 0; k < UN; ++k) {
-                                    u32 none = 0u;
-                                    warp_push1(cand[k] ? 2u : 0u, word[k], pdv[k], lane, nsv, nsd, ncnt, scap, fv, fd, &s_far_cnt[f],
-                                               &s_far_min[f], fcap, &s_overflow, none);
-                                }
-                            }
-                        }
-                        // nodes with more than kEllWidth arcs: lane 0 of the group walks the rest of the CSR row
-#pragma unroll
-                        for (int k = 0; k < UN; ++k) {
-                            if (__any_sync(0xffffffffu, ovf[k])) {
-                                const u32 u = ent[k] & kNodeMask;
-                                u32 e = 0, re = 0;
-                                if (ovf[k]) { e = __ldg(p.row_ptr + u) + kEllWidth; re = __ldg(p.row_ptr + u + 1); }
-                                while (__any_sync(0xffffffffu, e < re)) {
-                                    u32 k1 = 0u, v1 = 0u;
-                                    u64 d1 = 0ull;
-                                    if (e < re) {
-                                        const Arc x = ld_arc(p.arcs + e);
-                                        v1 = x.col | kNoSkip;
-                                        d1 = (u64)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)du[k]), x.w));
-                                        if (d1 < ld_dist(dist + x.col)) {
-                                            const u64 o2 = atomicMin(dist + x.col, d1);
-                                            if (d1 < o2) k1 = hi32(d1) <= thr_hi ? 1u : 2u;
-                                        }
-                                        ++t_xarcs;
-                                        ++e;
-                                    }
-                                    warp_push1(k1, v1, d1, lane, nsv, nsd, ncnt, scap, fv, fd, &s_far_cnt[f], &s_far_min[f], fcap,
-                                               &s_overflow, t_push);
-                                }
-                            }
-                        }
-                    }
-                } else
                 for (u32 base = 0; base < n_s; base += BLOCK) {
                     const u32 i = base + tid;
                     bool valid = i < n_s;
@@ -619,13 +455,12 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024
                     for (int j = 0; j < kEllWidth; ++j) { kind[j] = 0u; pv[j] = 0u; pd[j] = 0ull; }
                     bool ovf = false;
                     if (valid) {
-                        if (i < scap) { u = qc.sv[i]; du = qc.sd[i]; }
-                        else { u = qc.gv[i - scap]; du = qc.gd[i - scap]; }
+                        if (i < scap) { u = csv[i]; du = csd[i]; }
+                        else { u = wv[cur_off + i]; du = wd[cur_off + i]; }
                         valid = expand_entry(p.ell, dist, u, du, thr_hi, p.preread, kind, pv, pd, ovf);
                         if (valid) { ++c_pop; c_relax += kEllWidth; } else ++c_stale;
                     }
-                    warp_push<kEllWidth>(kind, pv, pd, lane, qn, &s_cnt[cn], scap, gcap, fv, fd, &s_far_cnt[f],
-                                         &s_far_min[f], fcap, &s_overflow, c_push);
+                    warp_push<kEllWidth>(kind, pv, pd, lane, tg, &s_cnt[cn], &s_far_cnt[f], &s_far_min[f], &s_overflow, c_push);
                     // nodes with more than kEllWidth arcs: the rest of the CSR row, one arc per step
                     if (__any_sync(0xffffffffu, ovf)) {
                         u32 e = 0, re = 0;
@@ -644,8 +479,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024
                                 ++c_relax;
                                 ++e;
                             }
-                            warp_push<1>(k1, v1, d1, lane, qn, &s_cnt[cn], scap, gcap, fv, fd, &s_far_cnt[f],
-                                         &s_far_min[f], fcap, &s_overflow, c_push);
+                            warp_push<1>(k1, v1, d1, lane, tg, &s_cnt[cn], &s_far_cnt[f], &s_far_min[f], &s_overflow, c_push);
                         }
                     }
                 }
@@ -654,13 +488,19 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024
                 b ^= 1u;
                 continue;
             }
-            // ------------------------- near queue empty: advance the bucket -------------------------
+            // ------------------------- near queue empty (or thin): advance the bucket -------------------------
+            // every thread must have read s_cnt[c] before the split starts refilling that queue; past this barrier no
+            // push is in flight, so the far pile's counters are stable
+            __syncthreads();
             const u32 nf_raw = s_far_cnt[f];
-            if (nf_raw == 0u) break;                                    // tree complete
+            if (nf_raw == 0u) {
+                if (n == 0u) break;                                     // tree complete
+                force_round = true;                                     // nothing to admit yet
+                continue;
+            }
             const u32 nf = nf_raw < fcap ? nf_raw : fcap;
             const u32 far_min_hi = s_far_min[f];
-            // every thread must have seen s_cnt[c] == 0 before the split starts refilling that queue
-            __syncthreads();
+            rib = 0;
             if (tid == 0) s_stat[0] += 1u;
             // new threshold: smallest (lower bound of a) distance in the pile + delta
             const double lo = __longlong_as_double((long long)((u64)far_min_hi << 32));
@@ -679,27 +519,19 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024
                 thr_hi = hi32((u64)__double_as_longlong(__dadd_rn(lo, delta * dmul)));
             }
             const u32 fo = f ^ 1u;
-            const u32 *srcv = far_v(f);
-            const u64 *srcd = far_d(f);
-            const Queue qb = near_q(b);
-            u32 *const dv = far_v(fo);
-            u64 *const dd = far_d(fo);
+            const u32 src_off = 2u * gcap + f * fcap;
+            const PushTarget tg = target(b, fo);
             for (u32 base = 0; base < nf; base += BLOCK) {
                 const u32 i = base + tid;
                 u32 k1[1] = {0u}, v1[1] = {0u};
                 u64 d1[1] = {0ull};
                 if (i < nf) {
-                    v1[0] = srcv[i];
-                    d1[0] = srcd[i];
+                    v1[0] = wv[src_off + i];
+                    d1[0] = wd[src_off + i];
                     k1[0] = hi32(d1[0]) <= thr_hi ? 1u : 2u;
                 }
                 // the round after this reads (b, c); kept entries go to the other pile (never more than nf)
-                if constexpr (UN > 0)
-                    warp_push1(k1[0], v1[0], d1[0], lane, sv0 + b * scap, sd0 + b * scap, &s_cnt[c], scap, dv, dd, &s_far_cnt[fo],
-                               &s_far_min[fo], fcap, &s_overflow, t_push);
-                else
-                    warp_push<1>(k1, v1, d1, lane, qb, &s_cnt[c], scap, gcap, dv, dd, &s_far_cnt[fo],
-                                 &s_far_min[fo], fcap, &s_overflow, c_push);
+                warp_push<1>(k1, v1, d1, lane, tg, &s_cnt[c], &s_far_cnt[fo], &s_far_min[fo], &s_overflow, c_push);
             }
             __syncthreads();
             if (tid == 0) { s_far_cnt[f] = 0u; s_far_min[f] = 0xFFFFFFFFu; s_bucket_rounds = 0u; s_bucket_entries = 0u; }
@@ -708,10 +540,6 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024
             // and a relaxation round (with its barrier) always intervenes.
         }
 
-        if constexpr (UN > 0) {
-            c_pop += t_pop; c_stale += t_stale; c_push += t_push;
-            c_relax += (u64)t_pop * kEllWidth + t_xarcs;
-        }
         // ---- safety net: a queue overflowed and entries were dropped.  Sweep all
         // nodes Bellman-Ford style until nothing changes (same fixed point).
         if (s_overflow) {
@@ -749,299 +577,6 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024
         u64 v = vals[j];
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         if (lane == 0 && v) atomicAdd(p.counters + ids[j], v);
-    }
-}
-
-// ---------------------------------------------------------------------------
-// K2, warp-autonomous variant (option sssp_variant = 2).  Same near-far schedule, same entries, same
-// expansion code (expand_entry) and therefore the same fixed point, but inside a bucket the warps of
-// the CTA do not meet: every warp owns a ring of frontier entries in shared memory (head / tail live in
-// registers, no atomics), refills it with 32-entry chunks of the far pile (one shared-memory atomic per
-// chunk; entries beyond the threshold are copied straight to the other pile) and expands 32 entries per
-// pass until the ring and the pile are empty.  The CTA synchronises twice per BUCKET instead of once per
-// relaxation round, every pass but a warp's last runs on full warps, and the separate split pass over
-// the far pile is gone.  Near pushes stay with the warp that made them (bounded imbalance: a bucket is
-// dealt out again chunk by chunk at every advance); far pushes go to the shared pile.
-// ---------------------------------------------------------------------------
-template <int N>
-__device__ __forceinline__ void ring_push(const u32 (&kind)[N], const u32 (&pv)[N], const u64 (&pd)[N], u32 lane, u32 *rv, u64 *rd,
-                                          u32 wmask, u32 head, u32 &tail, u32 *far_v, u64 *far_d, u32 *far_cnt, u32 fcap,
-                                          u32 &my_min, u32 *overflow, u64 &c_push)
-{
-    u32 packed = 0;
-#pragma unroll
-    for (int j = 0; j < N; ++j) packed += (kind[j] & 1u) | ((kind[j] & 2u) << 15);     // near count low half, far count high half
-    u32 incl = packed;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
-        if ((int)lane >= o) incl += t;
-    }
-    const u32 total = __shfl_sync(0xffffffffu, incl, 31);
-    if (total == 0u) return;                                   // warp-uniform
-    const u32 tn = total & 0xFFFFu, tf = total >> 16;
-    const u32 space = (wmask + 1u) - (tail - head);
-    const u32 fit = tn < space ? tn : space;                   // near entries that find room in the ring
-    const u32 nfar = tf + (tn - fit);                          // the rest joins the far pile (comes back at the next advance)
-    const u32 excl = incl - packed;
-    u32 on = excl & 0xFFFFu, of = excl >> 16;
-    u32 bf = 0;
-    if (nfar) {                                                // warp-uniform
-        u32 mymin = 0xFFFFFFFFu, k = on;
-#pragma unroll
-        for (int j = 0; j < N; ++j) {
-            if (kind[j] == 2u || (kind[j] == 1u && k >= fit)) mymin = min(mymin, hi32(pd[j]));
-            k += kind[j] & 1u;
-        }
-        const u32 wmin = __reduce_min_sync(0xffffffffu, mymin);
-        my_min = min(my_min, wmin);
-        if (lane == 31) bf = atomicAdd(far_cnt, nfar);
-        bf = __shfl_sync(0xffffffffu, bf, 31);
-    }
-#pragma unroll
-    for (int j = 0; j < N; ++j) {
-        if (kind[j] == 1u) {
-            if (on < fit) {
-                const u32 q = (tail + on) & wmask;
-                rv[q] = pv[j];
-                rd[q] = pd[j];
-            } else {
-                const u32 idx = bf + tf + (on - fit);
-                if (idx < fcap) { far_v[idx] = pv[j]; far_d[idx] = pd[j]; } else *overflow = 1u;
-            }
-            ++on;
-        } else if (kind[j] == 2u) {
-            const u32 idx = bf + of;
-            if (idx < fcap) { far_v[idx] = pv[j]; far_d[idx] = pd[j]; } else *overflow = 1u;
-            ++of;
-        }
-    }
-    tail += fit;
-    c_push += (packed & 0xFFFFu) + (packed >> 16);
-}
-
-template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024 / BLOCK : 1)) sssp_warpq_kernel(SsspParams p)
-{
-    static_assert(BLOCK % 32 == 0, "whole warps");
-    constexpr u32 NW = BLOCK / 32;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const u32 wcap = p.near_scap;                  // ring entries per warp (power of two)
-    const u32 wmask = wcap - 1u;
-    const u32 gcap = p.near_gcap, fcap = p.far_cap;
-    const u32 tid = threadIdx.x;
-    const u32 lane = tid & 31u;
-    const u32 wid = tid >> 5;
-    u64 *const rd = reinterpret_cast<u64 *>(smem_raw) + (size_t)wid * wcap;
-    u32 *const rv = reinterpret_cast<u32 *>(reinterpret_cast<u64 *>(smem_raw) + (size_t)NW * wcap) + (size_t)wid * wcap;
-    __shared__ u32 s_far_cnt[2];
-    __shared__ u32 s_far_min[2];       // min high word among the entries of each far pile
-    __shared__ u32 s_chunk[2];         // next 32-entry chunk of the pile being consumed (by bucket parity)
-    __shared__ u32 s_be[2];            // entries expanded in the bucket (by bucket parity)
-    __shared__ int s_root_idx;
-    __shared__ u32 s_overflow;
-    __shared__ u32 s_changed;
-    __shared__ u32 s_stat[3];          // bucket advances, expansion passes, fallback sweeps
-
-    const u32 V = p.V;
-    const size_t ws_stride = (size_t)2 * gcap + (size_t)2 * fcap;          // same workspace layout as the round-based kernel
-    u32 *const wv = p.ws_v + (size_t)blockIdx.x * ws_stride + 2 * (size_t)gcap;
-    u64 *const wd = p.ws_d + (size_t)blockIdx.x * ws_stride + 2 * (size_t)gcap;
-
-    if (tid == 0) { s_stat[0] = 0u; s_stat[1] = 0u; s_stat[2] = 0u; }
-
-    for (;;) {
-        __syncthreads();                       // previous tree fully retired before s_* are reused
-        if (tid == 0) s_root_idx = (int)atomicAdd(p.work_counter, 1u);
-        __syncthreads();
-        const int ri = s_root_idx;
-        if (ri >= p.n_roots) break;
-        u64 *dist = p.dist_pool + (size_t)ri * p.slot_stride;
-        const u32 root = (u32)p.roots[ri];
-        {
-            ulonglong2 *d2 = reinterpret_cast<ulonglong2 *>(dist);
-            const u32 n2 = (u32)(p.slot_stride >> 1);
-            const ulonglong2 inf2 = make_ulonglong2(kInfBits, kInfBits);
-            for (u32 i = tid; i < n2; i += BLOCK) d2[i] = inf2;
-        }
-        if (tid == 0) {
-            s_far_cnt[0] = 0u; s_far_cnt[1] = 0u;
-            s_far_min[0] = 0xFFFFFFFFu; s_far_min[1] = 0xFFFFFFFFu;
-            s_chunk[0] = 0u; s_chunk[1] = 0u;
-            s_be[0] = 0u; s_be[1] = 0u;
-            s_overflow = 0u;
-            rv[0] = root | kNoSkip; rd[0] = 0ull;          // warp 0's ring
-        }
-        u32 head = 0, tail = wid == 0 ? 1u : 0u;            // warp-uniform
-        __syncthreads();
-        if (tid == 0) dist[root] = 0ull;                    // after the fill
-        __syncthreads();
-
-        double dmul = 1.0;                                  // adaptive multiplier of the bucket width
-        u32 f = 0, par = 0, nf = 0;                         // pile being consumed, bucket parity, entries in that pile
-        u32 thr_hi;
-        {
-            double delta = p.delta_scale * __ldg(p.wsum);
-            thr_hi = hi32((u64)__double_as_longlong(delta > 0.0 ? delta : 0.0));
-        }
-        u32 my_passes = 0;
-        u32 c_pop = 0, c_stale = 0, c_xarcs = 0;            // per tree and thread; folded into the global counters below
-        u64 c_push = 0;
-
-        for (;;) {                                          // one bucket per iteration
-            const u32 *const rfv = wv + (size_t)f * fcap;
-            const u64 *const rfd = wd + (size_t)f * fcap;
-            u32 *const wfv = wv + (size_t)(f ^ 1u) * fcap;
-            u64 *const wfd = wd + (size_t)(f ^ 1u) * fcap;
-            u32 *const wcnt = &s_far_cnt[f ^ 1u];
-            u32 my_min = 0xFFFFFFFFu, my_cnt = 0;
-            bool more = nf > 0u;
-            for (;;) {
-                __syncwarp();
-                const u32 cnt = tail - head;
-                if (cnt < 32u && more) {
-                    // refill: next chunk of the pile; entries beyond the threshold move to the other pile
-                    u32 ch = 0;
-                    if (lane == 0) ch = atomicAdd(&s_chunk[par], 1u);
-                    ch = __shfl_sync(0xffffffffu, ch, 0);
-                    if (ch * 32u >= nf) { more = false; continue; }
-                    const u32 i = ch * 32u + lane;
-                    u32 k1[1] = {0u}, v1[1] = {0u};
-                    u64 d1[1] = {0ull};
-                    if (i < nf) {
-                        v1[0] = rfv[i];
-                        d1[0] = rfd[i];
-                        k1[0] = hi32(d1[0]) <= thr_hi ? 1u : 2u;
-                    }
-                    ring_push<1>(k1, v1, d1, lane, rv, rd, wmask, head, tail, wfv, wfd, wcnt, fcap, my_min, &s_overflow, c_push);
-                    continue;
-                }
-                if (cnt == 0u) break;                       // pile dealt out and ring empty: this warp is done with the bucket
-                const u32 m = cnt < 32u ? cnt : 32u;
-                bool valid = lane < m;
-                u32 u = 0;
-                u64 du = 0;
-                if (valid) {
-                    const u32 q = (head + lane) & wmask;
-                    u = rv[q];
-                    du = rd[q];
-                }
-                head += m;
-                my_cnt += m;
-                ++my_passes;
-                u32 kind[kEllWidth], pv[kEllWidth];
-                u64 pd[kEllWidth];
-#pragma unroll
-                for (int j = 0; j < kEllWidth; ++j) { kind[j] = 0u; pv[j] = 0u; pd[j] = 0ull; }
-                bool ovf = false;
-                if (valid) {
-                    valid = expand_entry(p.ell, dist, u, du, thr_hi, p.preread, kind, pv, pd, ovf);
-                    if (valid) ++c_pop; else ++c_stale;
-                }
-                __syncwarp();                               // ring slots just read may be overwritten below
-                ring_push<kEllWidth>(kind, pv, pd, lane, rv, rd, wmask, head, tail, wfv, wfd, wcnt, fcap, my_min, &s_overflow, c_push);
-                // nodes with more than kEllWidth arcs: the rest of the CSR row, one arc per step
-                if (__any_sync(0xffffffffu, ovf)) {
-                    u32 e = 0, re = 0;
-                    if (ovf) { e = __ldg(p.row_ptr + (u & kNodeMask)) + kEllWidth; re = __ldg(p.row_ptr + (u & kNodeMask) + 1); }
-                    while (__any_sync(0xffffffffu, e < re)) {
-                        u32 k1[1] = {0u}, v1[1] = {0u};
-                        u64 d1[1] = {0ull};
-                        if (e < re) {
-                            const Arc x = ld_arc(p.arcs + e);
-                            v1[0] = x.col | kNoSkip;
-                            d1[0] = (u64)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)du), x.w));
-                            if (d1[0] < ld_dist(dist + x.col)) {
-                                const u64 o2 = atomicMin(dist + x.col, d1[0]);
-                                if (d1[0] < o2) k1[0] = hi32(d1[0]) <= thr_hi ? 1u : 2u;
-                            }
-                            ++c_xarcs;
-                            ++e;
-                        }
-                        ring_push<1>(k1, v1, d1, lane, rv, rd, wmask, head, tail, wfv, wfd, wcnt, fcap, my_min, &s_overflow, c_push);
-                    }
-                }
-            }
-            // ---- bucket end: the warps meet, agree on the next threshold, swap the piles
-            if (lane == 0) {
-                if (my_min != 0xFFFFFFFFu) atomicMin(&s_far_min[f ^ 1u], my_min);
-                if (my_cnt) atomicAdd(&s_be[par], my_cnt);
-            }
-            __syncthreads();
-            const u32 nf_raw = s_far_cnt[f ^ 1u];
-            if (nf_raw == 0u) break;                                    // tree complete (uniform)
-            const u32 far_min_hi = s_far_min[f ^ 1u];
-            const u32 be = s_be[par];
-            if (tid == 0) {
-                s_far_cnt[f] = 0u; s_far_min[f] = 0xFFFFFFFFu;          // the pile just consumed is the next push target
-                s_chunk[par ^ 1u] = 0u; s_be[par ^ 1u] = 0u;
-                s_stat[0] += 1u;
-            }
-            nf = nf_raw < fcap ? nf_raw : fcap;
-            const double lo = __longlong_as_double((long long)((u64)far_min_hi << 32));
-            if (p.adaptive) {
-                // bucket width follows the wave: widen while a bucket cannot keep the CTA's warps busy for a few
-                // passes each, narrow again when it floods them
-                if (be < 4u * BLOCK && dmul < 16.0) dmul *= 1.5;
-                else if (be > 32u * BLOCK && dmul > 1.0) dmul *= (1.0 / 1.5);
-            }
-            {
-                double delta = p.delta_scale * __ldg(p.wsum);
-                if (!(delta > 0.0)) delta = 0.0;
-                thr_hi = hi32((u64)__double_as_longlong(__dadd_rn(lo, delta * dmul)));
-            }
-            f ^= 1u;
-            par ^= 1u;
-            __syncthreads();
-        }
-        if (lane == 0 && my_passes) atomicAdd(&s_stat[1], my_passes);
-        {
-            // one atomic per warp, counter and tree
-            u32 v3[4] = {c_pop, c_stale, c_xarcs, (u32)c_push};
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                for (int o = 16; o > 0; o >>= 1) v3[j] += __shfl_xor_sync(0xffffffffu, v3[j], o);
-            if (lane == 0) {
-                if (v3[0]) { atomicAdd(p.counters + C_NODES_POPPED, (u64)v3[0]); }
-                if (v3[0] | v3[2]) atomicAdd(p.counters + C_ARCS_RELAXED, (u64)v3[0] * kEllWidth + v3[2]);
-                if (v3[1]) atomicAdd(p.counters + C_STALE_POPS, (u64)v3[1]);
-                if (v3[3]) atomicAdd(p.counters + C_PUSHES, (u64)v3[3]);
-            }
-        }
-
-        // ---- safety net: a pile overflowed and entries were dropped.  Sweep all nodes Bellman-Ford
-        // style until nothing changes (same fixed point).
-        if (s_overflow) {
-            for (;;) {
-                __syncthreads();
-                if (tid == 0) { s_changed = 0u; s_stat[2] += 1u; }
-                __syncthreads();
-                bool any = false;
-                for (u32 u = tid; u < V; u += BLOCK) {
-                    const u64 du = ld_dist(dist + u);
-                    if (du >= kInfBits) continue;
-                    const u32 rb = __ldg(p.row_ptr + u), re = __ldg(p.row_ptr + u + 1);
-                    for (u32 e = rb; e < re; ++e) {
-                        const Arc x = ld_arc(p.arcs + e);
-                        const u64 ndb = (u64)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)du), x.w));
-                        if (ndb < ld_dist(dist + x.col)) {
-                            atomicMin(dist + x.col, ndb);
-                            any = true;
-                        }
-                    }
-                }
-                if (any) s_changed = 1u;
-                __syncthreads();
-                if (!s_changed) break;
-            }
-        }
-    }
-
-    __syncthreads();
-    if (tid == 0) {
-        if (s_stat[0]) atomicAdd(p.counters + C_ADVANCES, (u64)s_stat[0]);
-        if (s_stat[1]) atomicAdd(p.counters + C_ROUNDS, (u64)s_stat[1]);
-        if (s_stat[2]) atomicAdd(p.counters + C_FALLBACK_SWEEPS, (u64)s_stat[2]);
     }
 }
 
