@@ -100,8 +100,8 @@ int s4_ctx_sync(s4_ctx *ctx);
  *   "block_threads"      0 (default: from the graph's wave width) | 32 | 64 | 128 | 256 | 512 | 1024
  *   "ctas_per_sm"        0 (default: 1024 threads per SM)
  *   "near_smem_entries"  0 (default: 6 per thread) - shared-memory part of each near queue
- *   "queue_entries"      0 (default: from V) - per-CTA spill / far-pile capacity
- *   "pool_bytes"         bytes for the per-tree distance arrays (default 64e9, capped by free memory)
+ *   "queue_entries"      0 (default: from V, within 15 % of the free device memory) - per-CTA spill / far-pile capacity
+ *   "pool_bytes"         cap on the bytes of per-tree distance arrays (default 0: 55 % of the free device memory)
  *   "batch_roots"        0 (default: from pool_bytes) - trees in flight
  *   "root_mode"          S4_ROOT_* used by the next s4_sim_create
  *   "walk_tile"          0 (default: 8) | 4 | 8 | 16 | 32 lanes per walking trip

@@ -57,7 +57,7 @@ struct Options {
     int near_smem_entries = 0;      // 0 = 6 entries per thread
     int64_t queue_entries = 0;      // 0 = auto (from V)
     int64_t batch_roots = 0;        // 0 = auto (from pool_bytes)
-    double pool_bytes = 64.0e9;
+    double pool_bytes = 0.0;        // cap on the bytes of per-tree distance arrays; 0 = 55 % of the free device memory
     int root_mode = S4_ROOT_ORIGIN;
     int walk_tile = 0;              // lanes per walking trip; 0 = from the graph's degrees
     int lanes = 2;                  // concurrent (SSSP launch -> walk) lanes per day; 1 = strictly serial kernels
@@ -129,6 +129,7 @@ struct s4_graph {
     DevBuf<u32> ws_v;          // per-CTA frontier workspace (entry words / distances), two lanes
     DevBuf<u64> ws_d;
     int ws_ctas = 0;
+    bool ws_auto = false;      // workspace sized by the library (not by the "queue_entries" option)
     u32 near_gcap = 0, far_cap = 0;
     DevBuf<u32> work_counters;
     // single-source API scratch
@@ -538,18 +539,33 @@ struct SsspLaunch {
     u32 scap = 0;
 };
 
+// Device memory the scratch of a graph may take: the pool of per-tree distance arrays (55 % of what is free,
+// or the "pool_bytes" option if that is smaller) and the per-CTA frontier workspace (15 %).
+static int scratch_budget(s4_graph *g, double *pool_budget, double *ws_budget)
+{
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    double avail = (double)free_b;
+    if (g->pool.p) avail += (double)(g->pool.n * sizeof(u64));
+    if (g->ws_v.p) avail += (double)(g->ws_v.n * sizeof(u32));
+    if (g->ws_d.p) avail += (double)(g->ws_d.n * sizeof(u64));
+    const Options &o = g->ctx->opt;
+    *pool_budget = o.pool_bytes > 0.0 ? std::min(o.pool_bytes, 0.55 * avail) : 0.55 * avail;
+    *ws_budget = 0.15 * avail;
+    return S4_OK;
+}
+
 static int plan_sssp(s4_graph *g, SsspLaunch *L)
 {
     const Options &o = g->ctx->opt;
     int block = o.block_threads ? o.block_threads : g->auto_block;
     if (!o.block_threads) {
         // narrow CTAs only pay off when that many trees fit in flight: each needs a distance slot (8 B x V)
-        size_t free_b = 0, total_b = 0;
-        CU(cudaMemGetInfo(&free_b, &total_b));
-        if (g->pool.p) free_b += g->pool.n * sizeof(u64);
+        double pool_budget = 0.0, ws_budget = 0.0;
+        int rc = scratch_budget(g, &pool_budget, &ws_budget);
+        if (rc) return rc;
         const double per_slot = 8.0 * (double)g->V;
-        const int64_t slots = o.batch_roots > 0 ? o.batch_roots
-                                                : (int64_t)(std::min(o.pool_bytes, 0.6 * (double)free_b) / per_slot);
+        const int64_t slots = o.batch_roots > 0 ? o.batch_roots : (int64_t)(pool_budget / per_slot);
         const int64_t per_lane = std::max<int64_t>(1, slots / 2);
         while (block < 1024 && (int64_t)g->ctx->prop.multiProcessorCount * std::min(32, 1024 / block) > per_lane) block *= 2;
     }
@@ -573,12 +589,12 @@ static int ensure_scratch(s4_graph *g, const SsspLaunch &L, int64_t slots_wanted
 {
     const Options &o = g->ctx->opt;
     const int64_t V = g->V;
-    int64_t slots = o.batch_roots > 0 ? o.batch_roots : (int64_t)(o.pool_bytes / (8.0 * (double)V));
-    size_t free_b = 0, total_b = 0;
-    CU(cudaMemGetInfo(&free_b, &total_b));
-    if (g->pool.p) free_b += g->pool.n * sizeof(u64);
-    const int64_t by_mem = (int64_t)((double)free_b * 0.6 / (8.0 * (double)V));
-    slots = std::max<int64_t>(1, std::min(std::min(slots, by_mem), slots_wanted));
+    double pool_budget = 0.0, ws_budget = 0.0;
+    int rc = scratch_budget(g, &pool_budget, &ws_budget);
+    if (rc) return rc;
+    const int64_t by_mem = (int64_t)(pool_budget / (8.0 * (double)V));
+    int64_t slots = o.batch_roots > 0 ? std::min<int64_t>(o.batch_roots, by_mem) : by_mem;
+    slots = std::max<int64_t>(1, std::min(slots, slots_wanted));
     if (slots > g->pool_slots || !g->pool.p) {
         CU(g->pool.alloc((size_t)slots * (size_t)((V + 3) & ~(int64_t)3)));
         g->pool_slots = slots;
@@ -588,12 +604,23 @@ static int ensure_scratch(s4_graph *g, const SsspLaunch &L, int64_t slots_wanted
     int64_t q = o.queue_entries > 0 ? o.queue_entries
                                     : std::max<int64_t>(8192, std::max<int64_t>(65536, V / 4) * std::min(L.block, 256) / 256);
     q = std::min<int64_t>(q, std::max<int64_t>(V, 1024) * 2);
-    if (L.grid > g->ws_ctas || (u32)q != g->near_gcap || !g->ws_v.p) {
+    if (o.queue_entries <= 0) {
+        // many narrow CTAs on a large graph: keep the whole workspace (two lanes x CTAs x four queues x 12 B) inside
+        // its share of the device memory; a wave is far thinner than V / 4 on road graphs
+        const double per_entry = 2.0 * (double)L.grid * 4.0 * (double)(sizeof(u32) + sizeof(u64));
+        q = std::max<int64_t>(8192, std::min<int64_t>(q, (int64_t)(ws_budget / per_entry)));
+    }
+    // an automatically sized workspace is kept while it is large enough (its budget moves with the free memory)
+    const bool explicit_q = o.queue_entries > 0;
+    if (L.grid > g->ws_ctas || !g->ws_v.p || (explicit_q ? (u32)q != g->near_gcap : !g->ws_auto)) {
+        g->ws_v.release();
+        g->ws_d.release();
         CU(g->ws_v.alloc((size_t)2 * L.grid * 4 * (size_t)q));      // two lanes (concurrent launches)
         CU(g->ws_d.alloc((size_t)2 * L.grid * 4 * (size_t)q));
         g->ws_ctas = L.grid;
         g->near_gcap = (u32)q;
         g->far_cap = (u32)q;
+        g->ws_auto = !explicit_q;
     }
     return S4_OK;
 }

@@ -146,7 +146,10 @@ def test_road_construction_golden(dev, phys):
 @pytest.mark.parametrize("opts", [dict(), dict(block_threads=256, ctas_per_sm=4, delta_factor=0.5),
                                   dict(block_threads=1024, delta_factor=8.0, near_smem_entries=64),
                                   dict(delta_factor=0.0), dict(preread=1), dict(preread=1, near_smem_entries=64),
-                                  dict(block_threads=32, near_smem_entries=32, delta_factor=1.0)])
+                                  dict(block_threads=32, near_smem_entries=32, delta_factor=1.0),
+                                  # overlapped buckets: off, and so eager that nearly every advance finds entries pending
+                                  dict(early_advance=0), dict(early_advance=64, delta_factor=0.5),
+                                  dict(early_advance=64, block_threads=32, near_smem_entries=32)])
 @pytest.mark.parametrize("ranked", [False, True])
 def test_sssp_dist_and_pred_vs_oracle(dev, shape, opts, ranked):
     """Single trees: distances bit-equal to Dijkstra, predecessors equal under the canonical rule;
@@ -373,6 +376,8 @@ def test_c_abi_error_behaviour(dev, phys):
         dev.set_option("block_threads", 300)
     with pytest.raises(_ffi.S4Error):
         dev.set_option("no_such_option", 1)
+    with pytest.raises(Exception):
+        dev.set_option("early_advance", 65)
     sim = engine.DeviceSim(g, np.zeros(0, np.int32), np.zeros(0, np.int32), 0.1, phys)   # empty trip list
     sim.step()
     assert sim.get_load().tolist() == [0, 0]
