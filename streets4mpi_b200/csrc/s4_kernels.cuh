@@ -334,8 +334,8 @@ __device__ __forceinline__ void warp_push(const u32 (&kind)[N], const u32 (&pv)[
             if (is_near && idx < t.scap) { t.sv[idx] = pv[j]; t.sd[idx] = pd[j]; }
             else if (idx < (is_near ? t.near_lim : t.fcap)) {
                 const u32 off = (is_near ? t.near_off : t.far_off) + idx;
-                t.wv[off] = pv[j];
-                t.wd[off] = pd[j];
+                __stcs(t.wv + off, pv[j]);
+                __stcs(t.wd + off, pd[j]);
             } else *overflow = 1u;
         }
     }
@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024
             ulonglong2 *d2 = reinterpret_cast<ulonglong2 *>(dist);
             const u32 n2 = (u32)(p.slot_stride >> 1);
             const ulonglong2 inf2 = make_ulonglong2(kInfBits, kInfBits);
-            for (u32 i = tid; i < n2; i += BLOCK) d2[i] = inf2;
+            for (u32 i = tid; i < n2; i += BLOCK) __stcs(d2 + i, inf2);      // streaming: not needed again before the wave arrives
         }
         if (tid == 0) {
             s_cnt[0] = 1u; s_cnt[1] = 0u; s_cnt[2] = 0u;
@@ -526,8 +526,8 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024
                 u32 k1[1] = {0u}, v1[1] = {0u};
                 u64 d1[1] = {0ull};
                 if (i < nf) {
-                    v1[0] = wv[src_off + i];
-                    d1[0] = wd[src_off + i];
+                    v1[0] = __ldcs(wv + src_off + i);
+                    d1[0] = __ldcs(wd + src_off + i);
                     k1[0] = hi32(d1[0]) <= thr_hi ? 1u : 2u;
                 }
                 // the round after this reads (b, c); kept entries go to the other pile (never more than nf)
