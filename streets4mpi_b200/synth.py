@@ -70,6 +70,31 @@ def planar_arrays(n_nodes, seed=1, mean_degree=2.4, extent=None):
             "lon": pts[:, 0], "lat": pts[:, 1]}
 
 
+def ladder_arrays(rows, cols, seed=1, rung_fraction=0.2):
+    """Country-scale road-like graph in O(V) time and memory (BASELINE cfg5 shape: planar_arrays' Delaunay does not
+    scale to 5e7 points): every row of a rows x cols lattice is a street chain, and a seeded `rung_fraction` of the
+    vertical links joins neighbouring rows (at least one per pair of rows, so the graph is connected).  Mean degree
+    2 + 2 * rung_fraction (2.4 like real road graphs), jittered lengths, the usual speed mix; node id = r * cols + c."""
+    rng = np.random.default_rng(seed)
+    n = rows * cols
+    ids = np.arange(n, dtype=np.int64)
+    hu = ids[(ids % cols) != cols - 1]
+    hv = hu + 1
+    vu_all = ids[: n - cols]
+    keep = rng.random(len(vu_all)) < rung_fraction
+    keep[np.arange(rows - 1, dtype=np.int64) * cols + rng.integers(0, cols, size=rows - 1)] = True
+    vu = vu_all[keep]
+    vv = vu + cols
+    u = np.concatenate([hu, vu])
+    v = np.concatenate([hv, vv])
+    S = len(u)
+    length = rng.uniform(20.0, 400.0, size=S)
+    ms = rng.choice(SPEED_CLASSES, size=S, p=SPEED_WEIGHTS).astype(np.int32)
+    rr, cc = np.divmod(ids, cols)
+    return {"node_ids": ids, "u": u, "v": v, "length": length, "max_speed": ms,
+            "lon": cc.astype(np.float64), "lat": rr.astype(np.float64)}
+
+
 def network_from(arrays):
     return StreetNetwork.from_arrays(arrays["node_ids"], arrays["u"], arrays["v"], arrays["length"],
                                      arrays["max_speed"], arrays.get("lon"), arrays.get("lat"))
@@ -96,7 +121,7 @@ def trip_arrays(n_trips, origins, goals, seed):
 
 
 def parse_spec(spec):
-    """'synthetic:grid:ROWSxCOLS[:seed]' or 'synthetic:planar:N[:seed]' -> arrays"""
+    """'synthetic:grid:ROWSxCOLS[:seed]', 'synthetic:planar:N[:seed]' or 'synthetic:ladder:ROWSxCOLS[:seed]' -> arrays"""
     parts = spec.split(":")
     if len(parts) < 3 or parts[0] != "synthetic":
         raise ValueError("not a synthetic network spec: %r" % (spec,))
@@ -106,6 +131,9 @@ def parse_spec(spec):
         return grid_arrays(int(r), int(c), seed)
     if parts[1] == "planar":
         return planar_arrays(int(parts[2]), seed)
+    if parts[1] == "ladder":
+        r, c = parts[2].lower().split("x")
+        return ladder_arrays(int(r), int(c), seed)
     raise ValueError("unknown synthetic network kind %r" % (parts[1],))
 
 
