@@ -361,6 +361,18 @@ def test_queue_overflow_falls_back_to_sweeps(dev, phys, preread):
             dev.set_option(k, val)
 
 
+def test_options_from_environment(monkeypatch):
+    """S4MPI_OPTIONS="key=value,..." (the A/B hook of tools/ab_variants.sh) reaches s4_ctx_set_option."""
+    from streets4mpi_b200 import _ffi, engine
+    monkeypatch.setenv("S4MPI_OPTIONS", "early_advance=5, delta_factor=2.5")
+    d = engine.Device()
+    assert d.get_option("early_advance") == 5 and d.get_option("delta_factor") == 2.5
+    d.close()
+    monkeypatch.setenv("S4MPI_OPTIONS", "no_such_option=1")
+    with pytest.raises(_ffi.S4Error):
+        engine.Device()
+
+
 def test_c_abi_error_behaviour(dev, phys):
     from streets4mpi_b200 import _ffi, engine
     with pytest.raises(_ffi.S4Error):

@@ -180,6 +180,11 @@ def test_synthetic_generators():
     cats = synth.node_categories(g["node_ids"], seed=1)
     assert len(cats["goals"]) == 5 and set(cats["commercial"]) | set(cats["industrial"]) == set(cats["goals"])
     assert synth.parse_spec("synthetic:grid:4x5:9")["node_ids"].shape == (20,)
+    lad = synth.ladder_arrays(40, 50, seed=3)                      # cfg5 shape: street chains joined by sparse rungs
+    assert abs(2 * len(lad["u"]) / 2000 - 2.4) < 0.1 and lad["length"].min() >= 20
+    m = sp.coo_matrix((np.ones(len(lad["u"])), (lad["u"], lad["v"])), shape=(2000, 2000))
+    assert connected_components(m, directed=False)[0] == 1
+    assert len(synth.parse_spec("synthetic:ladder:6x7")["node_ids"]) == 42
 
 
 def test_rank_seeding_known_answers():
