@@ -168,12 +168,20 @@ __global__ void driving_speed_kernel(int64_t n, const double *length, const int3
 // pool.  A frontier entry is (node, exact distance it was pushed with): popping
 // needs nothing from memory before the arc fetch, and the entry is dropped when
 // dist[node] has improved since (superseded), so a node is expanded once per
-// surviving improvement.  One thread expands one node: four LDG.128 arc records
-// and the stale check in flight together, then four dist[head] loads (ld.cg),
-// then atomicMin on the u64 view.  Improved heads go to the next near queue
-// (shared memory, spilling to global) when below the bucket threshold, else to
-// the far pile (global); pushes are compacted with a warp scan and one
-// shared-memory atomic per warp and queue.
+// surviving improvement.  One thread expands one node: the 64-byte row as two
+// 256-bit loads and the 32-byte sector of dist[] holding the node (stale check,
+// neighbours in the same sector) in flight together, then one 8-byte filtering
+// read (ld.cg) per remaining head, then RED.MIN on the u64 view (fire and forget:
+// the push is decided on the filtering read).  Improved heads go to the next near
+// queue (shared memory, spilling to global) when below the bucket threshold, else
+// to the far pile (global); pushes are compacted with a warp scan and one
+// shared-memory atomic per warp and queue.  The next bucket is admitted as soon
+// as a round runs thin (overlapped buckets).
+//
+// What binds it (ncu): the L1TEX wavefront pipe -- every lane
+// of a scattered access is a wavefront of its own, ~10 per node (2 row + 1 sector
+// per popped entry, live or superseded; ~1.7 filtering reads and ~1.4 RED per
+// live entry) -- together with the dependent latency of a pass.
 //
 // The fixed point reached is schedule-independent and equals Dijkstra's:
 // dist[v] = min over neighbours of fl(dist[u] + w) with left-to-right rounding.
