@@ -110,6 +110,9 @@ int s4_ctx_sync(s4_ctx *ctx);
  *   "early_advance"      2 (default): the next bucket is admitted as soon as a relaxation round (not one of the first
  *                        two of its bucket) holds fewer entries than 2/8 of a CTA - the thinning tail of a bucket
  *                        overlaps the head of the next; 0: only when the near queue is empty
+ *   "walk_ell"           1 (default): the walk reads fixed-stride rows {head, street_index, weight} (one 64-byte
+ *                        read per hop, no row_ptr lookup; nodes with more than four arcs use the CSR); 0: CSR only.
+ *                        Read at s4_sim_create.
  *   "lanes"              2 (default): a day's batches alternate between two concurrent launch lanes;
  *                        1: strictly serial kernels (per-kernel timing)
  * No option changes a result. */

@@ -62,6 +62,7 @@ struct Options {
     int walk_tile = 0;              // lanes per walking trip; 0 = from the graph's degrees
     int lanes = 2;                  // concurrent (SSSP launch -> walk) lanes per day; 1 = strictly serial kernels
     int adaptive_delta = 1;         // widen / narrow the bucket with the wave
+    int walk_ell = 1;               // the walk reads fixed-stride rows (one dependent stage less per hop); 0: CSR only
     int early_advance = 2;          // admit the next bucket when a round has fewer entries than this many eighths of a CTA
                                     // (0 = only when the near queue is empty); measured on cfg3 and a planar graph
     int preread = 2;                // 1: filtering read, then returning atomicMin;
@@ -160,6 +161,7 @@ struct s4_sim {
     DevBuf<double> w_street;
     DevBuf<Arc> arcs;              // CSR records (walk, overflow arcs)
     DevBuf<Arc> ell;               // fixed-stride records (SSSP)
+    DevBuf<Arc> ellw;              // fixed-stride records with street indices (walk); empty when walk_ell = 0
     DevBuf<double> wsum;
     DevBuf<u64> counters;
     bool weights_valid = false;
@@ -260,6 +262,7 @@ static void option_slot(Options &o, const char *key, int *kind, void **raw)
         {"root_mode", 1, &o.root_mode},             {"walk_tile", 1, &o.walk_tile},
         {"preread", 1, &o.preread},                 {"lanes", 1, &o.lanes},
         {"adaptive_delta", 1, &o.adaptive_delta},   {"early_advance", 1, &o.early_advance},
+        {"walk_ell", 1, &o.walk_ell},
     };
     for (auto &it : items)
         if (strcmp(it.k, key) == 0) { *kind = it.kind; *raw = it.p; return; }
@@ -286,7 +289,7 @@ extern "C" int s4_ctx_set_option(s4_ctx *ctx, const char *key, double value)
               t.batch_roots >= 0 && t.pool_bytes >= 0.0 && t.root_mode >= 0 && t.root_mode <= 2 &&
               (t.walk_tile == 0 || t.walk_tile == 4 || t.walk_tile == 8 || t.walk_tile == 16 || t.walk_tile == 32) &&
               (t.preread == 1 || t.preread == 2) && (t.lanes == 1 || t.lanes == 2) &&
-              t.early_advance >= 0 && t.early_advance <= 64;
+              t.early_advance >= 0 && t.early_advance <= 64 && (t.walk_ell == 0 || t.walk_ell == 1);
     if (!ok) return fail(S4_ERR_ARG, "option '%s': value %g out of range", key, value);
     ctx->opt = trial;
     return S4_OK;
@@ -804,6 +807,7 @@ extern "C" int s4_sim_create(s4_graph *g, int64_t T, const int32_t *origin, cons
     CU(sim->w_street.alloc((size_t)std::max<int64_t>(S, 1)));
     CU(sim->arcs.alloc((size_t)std::max<int64_t>(A, 1)));
     CU(sim->ell.alloc((size_t)g->V * kEllWidth));
+    if (ctx->opt.walk_ell) CU(sim->ellw.alloc((size_t)g->V * kEllWidth));
     CU(sim->wsum.alloc(1));
     CU(sim->counters.alloc(C_COUNT));
     CU(cudaMemsetAsync(sim->load.p, 0, (size_t)std::max<int64_t>(S, 1) * sizeof(u32), st));   // simulation.py:43
@@ -959,6 +963,12 @@ static int run_weights(s4_sim *sim, int reset_load)
     weights_ell_kernel<<<grid_for((int64_t)g->V * kEllWidth, 256, ctx), 256, 0, st>>>((int64_t)g->V * kEllWidth, g->ell_cs.p,
                                                                                      sim->w_street.p, sim->ell.p);
     CU(cudaGetLastError());
+    if (sim->ellw.p) {
+        weights_ellw_kernel<<<grid_for((int64_t)g->V * kEllWidth, 256, ctx), 256, 0, st>>>((int64_t)g->V * kEllWidth, g->ell_cs.p,
+                                                                                          sim->w_street.p, sim->ellw.p);
+        CU(cudaGetLastError());
+        ++sim->acc.kernel_launches;
+    }
     ++sim->acc.kernel_launches;
     sim->weights_valid = true;
     return S4_OK;
@@ -1032,6 +1042,7 @@ extern "C" int s4_sim_step(s4_sim *sim)
         WalkParams wp;
         wp.row_ptr = g->row_ptr.p;
         wp.arcs = sim->arcs.p;
+        wp.ellw = ctx->opt.walk_ell ? sim->ellw.p : nullptr;
         wp.orig = g->orig.p;
         wp.slot_stride = (size_t)((g->V + 3) & ~3);
         wp.dist_pool = g->pool.p + (size_t)first_slot * wp.slot_stride;

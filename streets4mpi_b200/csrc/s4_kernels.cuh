@@ -146,6 +146,21 @@ __global__ void weights_ell_kernel(int64_t n_slots, const uint2 *__restrict__ el
     }
 }
 
+// fixed-stride rows for the walk: {head | overflow flag, street_index, w[street]} (padding: {self, -, +inf}); one
+// 64-byte read replaces the row_ptr -> arcs chain of the CSR
+__global__ void weights_ellw_kernel(int64_t n_slots, const uint2 *__restrict__ ell_cs, const double *__restrict__ w_street,
+                                    Arc *__restrict__ ellw)
+{
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n_slots; e += (int64_t)gridDim.x * blockDim.x) {
+        const uint2 cs = ell_cs[e];
+        Arc a;
+        a.col = cs.x;
+        a.street = cs.y & 0x1FFFFFFFu;
+        a.w = cs.y == 0xFFFFFFFFu ? __longlong_as_double((long long)0x7FF0000000000000ll) : w_street[cs.y & 0x1FFFFFFFu];
+        ellw[e] = a;
+    }
+}
+
 __global__ void driving_speed_kernel(int64_t n, const double *length, const int32_t *max_speed, const u32 *trips,
                                      Phys ph, double *out)
 {
@@ -665,6 +680,65 @@ __device__ __forceinline__ u64 canonical_pred(const cg::thread_block_tile<TILE> 
     return loose;
 }
 
+// The same rule on the fixed-stride rows (ellw: first kEllWidth arcs of every node, lane k of the tile looks at slot
+// k): one dependent memory stage less per hop than the CSR (no row_ptr lookup).  Nodes with more arcs fall back to
+// canonical_pred.  Padding slots point back at `cur` and are skipped like self loops.
+template <int TILE, bool WANT_ID>
+__device__ __forceinline__ u64 canonical_pred_ell(const cg::thread_block_tile<TILE> &tile, const Arc *__restrict__ ellw,
+                                                  const u32 *__restrict__ row_ptr, const Arc *__restrict__ arcs,
+                                                  const u32 *__restrict__ orig, const u64 *dist, u32 cur, u64 dv,
+                                                  u32 *col_out, u64 *du_out)
+{
+    static_assert(TILE >= kEllWidth, "one lane per slot");
+    const u32 lane = tile.thread_rank();
+    Arc a;
+    a.col = cur; a.street = 0u; a.w = 0.0;
+    if (lane < (u32)kEllWidth) a = ld_arc(ellw + (size_t)cur * kEllWidth + lane);
+    if (tile.any(lane == 0u && (a.col & kOvfBit) != 0u))
+        return canonical_pred<TILE, WANT_ID>(tile, row_ptr, arcs, orig, dist, cur, dv, col_out, du_out);
+    const u32 col = a.col;
+    u64 du = 0;
+    bool match = false;
+    if (lane < (u32)kEllWidth && col != cur) {
+        du = ld_dist(dist + col);
+        const u64 ndb = (u64)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)du), a.w));
+        match = du < kInfBits && ndb == dv;
+    }
+    const u32 mm = tile.ballot(match);
+    if (mm == 0u) { *du_out = 0; *col_out = 0; return ~0ull; }
+    if ((mm & (mm - 1u)) == 0u) {
+        // exactly one arc reproduces dist[cur] (unique shortest path): no id lookup needed for the walk
+        const u32 src = (u32)__ffs((int)mm) - 1u;
+        const u32 street = tile.shfl(a.street, src);
+        *col_out = tile.shfl(col, src);
+        *du_out = tile.shfl(du, src);
+        const u32 id_u = !WANT_ID ? 0u : orig ? __ldg(orig + *col_out) : *col_out;
+        return ((u64)id_u << 32) | street;
+    }
+    // ties: the full rule on the caller's ids
+    const u32 id_cur = orig ? __ldg(orig + cur) : cur;
+    u64 strict = ~0ull, loose = ~0ull, du_s = 0, du_l = 0;
+    u32 col_s = 0, col_l = 0;
+    if (match) {
+        const u32 id_u = orig ? __ldg(orig + col) : col;
+        const u64 key = ((u64)id_u << 32) | a.street;
+        loose = key; du_l = du; col_l = col;
+        if (du < dv || id_u < id_cur) { strict = key; du_s = du; col_s = col; }
+    }
+    for (int o = TILE / 2; o > 0; o >>= 1) {
+        const u64 ks = tile.shfl_xor(strict, o), ds = tile.shfl_xor(du_s, o);
+        const u32 cs = tile.shfl_xor(col_s, o);
+        if (ks < strict) { strict = ks; du_s = ds; col_s = cs; }
+        const u64 kl = tile.shfl_xor(loose, o), dl = tile.shfl_xor(du_l, o);
+        const u32 cl = tile.shfl_xor(col_l, o);
+        if (kl < loose) { loose = kl; du_l = dl; col_l = cl; }
+    }
+    if (strict != ~0ull) { *du_out = du_s; *col_out = col_s; return strict; }
+    *du_out = du_l;
+    *col_out = col_l;
+    return loose;
+}
+
 // ---------------------------------------------------------------------------
 // K3  simulation.py:78-88: one tile of lanes per trip walks target -> root up
 // the canonical predecessor tree (derived on the fly from the distance slot,
@@ -674,6 +748,7 @@ __device__ __forceinline__ u64 canonical_pred(const cg::thread_block_tile<TILE> 
 struct WalkParams {
     const u32 *row_ptr;
     const Arc *arcs;
+    const Arc *ellw;            // fixed-stride rows with street indices (nullptr: CSR only)
     const u32 *orig;            // device number -> caller's node id (nullptr = identity)
     const u64 *dist_pool;
     size_t slot_stride;
@@ -708,7 +783,8 @@ __global__ void __launch_bounds__(256) walk_kernel(WalkParams p)
         while (cur != root) {                                              // :83
             u64 du;
             u32 nxt;
-            const u64 key = canonical_pred<TILE, false>(tile, p.row_ptr, p.arcs, p.orig, dist, cur, dv, &nxt, &du);
+            const u64 key = p.ellw ? canonical_pred_ell<TILE, false>(tile, p.ellw, p.row_ptr, p.arcs, p.orig, dist, cur, dv, &nxt, &du)
+                                   : canonical_pred<TILE, false>(tile, p.row_ptr, p.arcs, p.orig, dist, cur, dv, &nxt, &du);
             if (key == ~0ull || ++guard > p.V) { ++c_stuck; break; }
             if (tile.thread_rank() == 0) atomicAdd(p.load + (u32)key, p.volume);   // :86-88
             ++c_hops;
