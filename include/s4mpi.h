@@ -149,6 +149,13 @@ int s4_graph_sssp(s4_graph *g, const double *w_street, int32_t origin, double *d
  * every reference rank owns its StreetNetwork. */
 int s4_sim_create(s4_graph *g, int64_t T, const int32_t *origin, const int32_t *goal,
                   double jam_tolerance, const s4_physics *phys, s4_sim **out);
+/* The same with the trips drawn on the device (tripgenerator.py:33-35: one uniform origin and one uniform goal per
+ * resident): trip t takes Philox4x32-10 at counter (t, 0) under key `seed`, words 0,1 index origins[], words 2,3
+ * goals[] (index = floor(r64 * n / 2^64)); only the two populations cross PCIe.  streets4mpi.py:67-75. */
+int s4_sim_create_sampled(s4_graph *g, int64_t T, int64_t n_origins, const int32_t *origins, int64_t n_goals,
+                          const int32_t *goals, uint64_t seed, double jam_tolerance, const s4_physics *phys, s4_sim **out);
+/* the simulation's T trips, grouped by tree root (origin_out[T], goal_out[T]) */
+int s4_sim_get_trips(s4_sim *sim, int32_t *origin_out, int32_t *goal_out);
 int s4_sim_free(s4_sim *sim);
 /* number of distinct tree roots and the root mode actually used */
 int s4_sim_roots(s4_sim *sim, int64_t *n_roots, int *root_mode);

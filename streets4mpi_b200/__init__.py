@@ -9,8 +9,8 @@ needs the built library and a CUDA device.
 from .settings import settings  # noqa: F401
 from .utils import merge_arrays  # noqa: F401
 from .streetnetwork import StreetNetwork  # noqa: F401
-from .tripgenerator import TripGenerator, TripTable  # noqa: F401
+from .tripgenerator import SampledTrips, TripGenerator, TripTable  # noqa: F401
 from .simulation import Simulation, calculate_driving_speed  # noqa: F401
 
-__all__ = ["settings", "merge_arrays", "StreetNetwork", "TripGenerator", "TripTable", "Simulation",
+__all__ = ["settings", "merge_arrays", "StreetNetwork", "TripGenerator", "TripTable", "SampledTrips", "Simulation",
            "calculate_driving_speed"]

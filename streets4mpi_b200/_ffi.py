@@ -60,6 +60,9 @@ SIGNATURES = {
     "s4_graph_sssp": (C.c_int, [_vp, _f64p, C.c_int32, _f64p, _i32p]),
     "s4_sim_create": (C.c_int, [_vp, C.c_int64, _i32p, _i32p, C.c_double, C.POINTER(Physics), C.POINTER(_vp)]),
     "s4_sim_free": (C.c_int, [_vp]),
+    "s4_sim_create_sampled": (C.c_int, [_vp, C.c_int64, C.c_int64, _i32p, C.c_int64, _i32p, C.c_uint64, C.c_double,
+                                        C.POINTER(Physics), C.POINTER(_vp)]),
+    "s4_sim_get_trips": (C.c_int, [_vp, _i32p, _i32p]),
     "s4_sim_roots": (C.c_int, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int)]),
     "s4_sim_step": (C.c_int, [_vp]),
     "s4_sim_weights": (C.c_int, [_vp, C.c_int, _f64p]),

@@ -762,44 +762,18 @@ static int64_t count_distinct_host(const int32_t *a, int64_t n, int32_t V)
     return d;
 }
 
-extern "C" int s4_sim_create(s4_graph *g, int64_t T, const int32_t *origin, const int32_t *goal, double jam_tolerance,
-                             const s4_physics *phys, s4_sim **out)
+// allocation and initial state shared by the two constructors
+static int sim_alloc(s4_graph *g, s4_sim *sim, int64_t T, double jam_tolerance, const s4_physics *phys, int mode)
 {
-    CHECK_ARG(g && out && phys, "s4_sim_create: NULL argument");
-    *out = nullptr;
-    CHECK_ARG(T >= 0 && T < (int64_t)1 << 31, "s4_sim_create: T out of range");
-    CHECK_ARG(T == 0 || (origin && goal), "s4_sim_create: NULL trip array");
-    CHECK_ARG(jam_tolerance == jam_tolerance, "s4_sim_create: jam_tolerance is NaN");
     s4_ctx *ctx = g->ctx;
-    CU(cudaSetDevice(ctx->device));
-    for (int64_t i = 0; i < T; ++i)
-        if (origin[i] < 0 || origin[i] >= g->V || goal[i] < 0 || goal[i] >= g->V)
-            return fail(S4_ERR_ARG, "trip %lld: node id out of range", (long long)i);
-    s4_sim *sim = new (std::nothrow) s4_sim();
-    if (!sim) return fail(S4_ERR_OOM, "host allocation failed");
-    struct Guard { s4_sim *s; ~Guard() { delete s; } } guard{sim};
+    cudaStream_t st = ctx->stream;
+    const int64_t S = g->S, A = g->A;
     sim->g = g;
     sim->T = T;
     sim->jam = jam_tolerance;
     sim->ph = Phys{phys->car_length, phys->min_breaking_distance, phys->braking_deceleration};
     sim->volume = phys->trip_volume;
-    int mode = ctx->opt.root_mode;
-    if (mode == S4_ROOT_AUTO)
-        mode = (T > 0 && count_distinct_host(goal, T, g->V) < count_distinct_host(origin, T, g->V)) ? S4_ROOT_GOAL : S4_ROOT_ORIGIN;
     sim->root_mode = mode;
-    const int32_t *root_h = mode == S4_ROOT_GOAL ? goal : origin;
-    const int32_t *target_h = mode == S4_ROOT_GOAL ? origin : goal;
-    std::vector<int32_t> root_m, target_m;
-    if (!g->rank.empty() && T > 0) {
-        root_m.resize((size_t)T);
-        target_m.resize((size_t)T);
-        for (int64_t i = 0; i < T; ++i) { root_m[(size_t)i] = g->rank[(size_t)root_h[i]]; target_m[(size_t)i] = g->rank[(size_t)target_h[i]]; }
-        root_h = root_m.data();
-        target_h = target_m.data();
-    }
-    cudaStream_t st = ctx->stream;
-    const int64_t S = g->S, A = g->A;
-
     CU(sim->load.alloc((size_t)std::max<int64_t>(S, 1)));
     CU(sim->cum.alloc((size_t)std::max<int64_t>(S, 1)));
     CU(sim->ms_vis.alloc((size_t)std::max<int64_t>(S, 1)));
@@ -818,54 +792,188 @@ extern "C" int s4_sim_create(s4_graph *g, int64_t T, const int32_t *origin, cons
         CU(cudaMemcpyAsync(sim->ms_vis.p, g->max_speed0.data(), (size_t)S * sizeof(int32_t), cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(sim->ms_ins.p, g->max_speed0.data(), (size_t)S * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     }
+    return S4_OK;
+}
 
-    // ---- group the trips by tree root on the device (tripgenerator.py:37-42)
-    if (T > 0) {
-        DevBuf<u32> kin, kout, vin, vout, flag, rank;
-        DevBuf<int64_t> off;
-        DevBuf<unsigned char> tmp;
-        CU(kin.alloc((size_t)T)); CU(kout.alloc((size_t)T)); CU(vin.alloc((size_t)T)); CU(vout.alloc((size_t)T));
-        CU(flag.alloc((size_t)T)); CU(rank.alloc((size_t)T));
-        CU(cudaMemcpyAsync(kin.p, root_h, (size_t)T * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(vin.p, target_h, (size_t)T * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-        int rc = cub_sort_pairs(ctx, tmp, kin.p, kout.p, vin.p, vout.p, T);
-        if (rc) return rc;
-        const int grid = grid_for(T, 256, ctx);
-        head_flag_kernel<<<grid, 256, 0, st>>>(T, (const int32_t *)kout.p, flag.p);
-        CU(cudaGetLastError());
-        size_t bytes = 0;
-        CU(cub::DeviceScan::InclusiveSum(nullptr, bytes, flag.p, rank.p, (int)T, st));
-        CU(tmp.ensure(bytes + 16));
-        CU(cub::DeviceScan::InclusiveSum(tmp.p, bytes, flag.p, rank.p, (int)T, st));
-        u32 D = 0;
-        CU(cudaMemcpyAsync(&D, rank.p + (T - 1), sizeof(u32), cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        sim->D = D;
-        CU(sim->roots.alloc((size_t)D));
-        CU(off.alloc((size_t)D + 1));
-        CU(sim->trip_root.alloc((size_t)T));
-        CU(sim->trip_target.alloc((size_t)T));
-        group_scatter_kernel<<<grid, 256, 0, st>>>(T, (const int32_t *)kout.p, flag.p, rank.p, sim->trip_root.p, sim->roots.p, off.p);
-        CU(cudaGetLastError());
-        CU(cudaMemcpyAsync(sim->trip_target.p, vout.p, (size_t)T * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
-        sim->h_root_off.resize((size_t)D + 1);
-        std::vector<int32_t> h_roots((size_t)D);
-        CU(cudaMemcpyAsync(sim->h_root_off.data(), off.p, (size_t)D * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(h_roots.data(), sim->roots.p, (size_t)D * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        sim->h_root_off[(size_t)D] = T;
-        for (u32 i = 0; i < D; ++i) {
-            const int32_t c = g->comp_of[(size_t)h_roots[i]];
-            sim->alg_arcs_per_day += g->comp_arcs[(size_t)c];
-            sim->alg_nodes_per_day += g->comp_nodes[(size_t)c];
-        }
-    } else {
+// group T trips (device arrays of root / target, device numbering) by tree root (tripgenerator.py:37-42)
+static int sim_group(s4_sim *sim, DevBuf<u32> &kin, DevBuf<u32> &vin)
+{
+    s4_graph *g = sim->g;
+    s4_ctx *ctx = g->ctx;
+    cudaStream_t st = ctx->stream;
+    const int64_t T = sim->T;
+    if (T == 0) {
         sim->h_root_off.assign(1, 0);
         CU(cudaStreamSynchronize(st));
+        return S4_OK;
     }
+    DevBuf<u32> kout, vout, flag, rank;
+    DevBuf<int64_t> off;
+    DevBuf<unsigned char> tmp;
+    CU(kout.alloc((size_t)T)); CU(vout.alloc((size_t)T));
+    CU(flag.alloc((size_t)T)); CU(rank.alloc((size_t)T));
+    int rc = cub_sort_pairs(ctx, tmp, kin.p, kout.p, vin.p, vout.p, T);
+    if (rc) return rc;
+    const int grid = grid_for(T, 256, ctx);
+    head_flag_kernel<<<grid, 256, 0, st>>>(T, (const int32_t *)kout.p, flag.p);
+    CU(cudaGetLastError());
+    size_t bytes = 0;
+    CU(cub::DeviceScan::InclusiveSum(nullptr, bytes, flag.p, rank.p, (int)T, st));
+    CU(tmp.ensure(bytes + 16));
+    CU(cub::DeviceScan::InclusiveSum(tmp.p, bytes, flag.p, rank.p, (int)T, st));
+    u32 D = 0;
+    CU(cudaMemcpyAsync(&D, rank.p + (T - 1), sizeof(u32), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    sim->D = D;
+    CU(sim->roots.alloc((size_t)D));
+    CU(off.alloc((size_t)D + 1));
+    CU(sim->trip_root.alloc((size_t)T));
+    CU(sim->trip_target.alloc((size_t)T));
+    group_scatter_kernel<<<grid, 256, 0, st>>>(T, (const int32_t *)kout.p, flag.p, rank.p, sim->trip_root.p, sim->roots.p, off.p);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(sim->trip_target.p, vout.p, (size_t)T * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    sim->h_root_off.resize((size_t)D + 1);
+    std::vector<int32_t> h_roots((size_t)D);
+    CU(cudaMemcpyAsync(sim->h_root_off.data(), off.p, (size_t)D * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h_roots.data(), sim->roots.p, (size_t)D * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    sim->h_root_off[(size_t)D] = T;
+    for (u32 i = 0; i < D; ++i) {
+        const int32_t c = g->comp_of[(size_t)h_roots[i]];
+        sim->alg_arcs_per_day += g->comp_arcs[(size_t)c];
+        sim->alg_nodes_per_day += g->comp_nodes[(size_t)c];
+    }
+    return S4_OK;
+}
+
+extern "C" int s4_sim_create(s4_graph *g, int64_t T, const int32_t *origin, const int32_t *goal, double jam_tolerance,
+                             const s4_physics *phys, s4_sim **out)
+{
+    CHECK_ARG(g && out && phys, "s4_sim_create: NULL argument");
+    *out = nullptr;
+    CHECK_ARG(T >= 0 && T < (int64_t)1 << 31, "s4_sim_create: T out of range");
+    CHECK_ARG(T == 0 || (origin && goal), "s4_sim_create: NULL trip array");
+    CHECK_ARG(jam_tolerance == jam_tolerance, "s4_sim_create: jam_tolerance is NaN");
+    s4_ctx *ctx = g->ctx;
+    CU(cudaSetDevice(ctx->device));
+    for (int64_t i = 0; i < T; ++i)
+        if (origin[i] < 0 || origin[i] >= g->V || goal[i] < 0 || goal[i] >= g->V)
+            return fail(S4_ERR_ARG, "trip %lld: node id out of range", (long long)i);
+    s4_sim *sim = new (std::nothrow) s4_sim();
+    if (!sim) return fail(S4_ERR_OOM, "host allocation failed");
+    struct Guard { s4_sim *s; ~Guard() { delete s; } } guard{sim};
+    int mode = ctx->opt.root_mode;
+    if (mode == S4_ROOT_AUTO)
+        mode = (T > 0 && count_distinct_host(goal, T, g->V) < count_distinct_host(origin, T, g->V)) ? S4_ROOT_GOAL : S4_ROOT_ORIGIN;
+    const int32_t *root_h = mode == S4_ROOT_GOAL ? goal : origin;
+    const int32_t *target_h = mode == S4_ROOT_GOAL ? origin : goal;
+    std::vector<int32_t> root_m, target_m;
+    if (!g->rank.empty() && T > 0) {
+        root_m.resize((size_t)T);
+        target_m.resize((size_t)T);
+        for (int64_t i = 0; i < T; ++i) { root_m[(size_t)i] = g->rank[(size_t)root_h[i]]; target_m[(size_t)i] = g->rank[(size_t)target_h[i]]; }
+        root_h = root_m.data();
+        target_h = target_m.data();
+    }
+    int rc = sim_alloc(g, sim, T, jam_tolerance, phys, mode);
+    if (rc) return rc;
+    DevBuf<u32> kin, vin;
+    if (T > 0) {
+        cudaStream_t st = ctx->stream;
+        CU(kin.alloc((size_t)T));
+        CU(vin.alloc((size_t)T));
+        CU(cudaMemcpyAsync(kin.p, root_h, (size_t)T * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(vin.p, target_h, (size_t)T * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    }
+    if ((rc = sim_group(sim, kin, vin))) return rc;
     guard.s = nullptr;
     ++g->refs;
     *out = sim;
+    return S4_OK;
+}
+
+// The trips are drawn on the device (sample_trips_kernel): only the two populations cross PCIe.
+extern "C" int s4_sim_create_sampled(s4_graph *g, int64_t T, int64_t n_origins, const int32_t *origins, int64_t n_goals,
+                                     const int32_t *goals, uint64_t seed, double jam_tolerance, const s4_physics *phys,
+                                     s4_sim **out)
+{
+    CHECK_ARG(g && out && phys, "s4_sim_create_sampled: NULL argument");
+    *out = nullptr;
+    CHECK_ARG(T >= 0 && T < (int64_t)1 << 31, "s4_sim_create_sampled: T out of range");
+    CHECK_ARG(T == 0 || (origins && goals && n_origins > 0 && n_goals > 0),
+              "s4_sim_create_sampled: empty population (random.sample raised ValueError there)");
+    CHECK_ARG(jam_tolerance == jam_tolerance, "s4_sim_create_sampled: jam_tolerance is NaN");
+    s4_ctx *ctx = g->ctx;
+    CU(cudaSetDevice(ctx->device));
+    for (int64_t i = 0; i < n_origins; ++i)
+        if (origins[i] < 0 || origins[i] >= g->V) return fail(S4_ERR_ARG, "origin %lld: node id out of range", (long long)i);
+    for (int64_t i = 0; i < n_goals; ++i)
+        if (goals[i] < 0 || goals[i] >= g->V) return fail(S4_ERR_ARG, "goal %lld: node id out of range", (long long)i);
+    s4_sim *sim = new (std::nothrow) s4_sim();
+    if (!sim) return fail(S4_ERR_OOM, "host allocation failed");
+    struct Guard { s4_sim *s; ~Guard() { delete s; } } guard{sim};
+    int mode = ctx->opt.root_mode;
+    if (mode == S4_ROOT_AUTO)                       // the smaller population bounds the number of distinct endpoints
+        mode = std::min<int64_t>(n_goals, T) < std::min<int64_t>(n_origins, T) ? S4_ROOT_GOAL : S4_ROOT_ORIGIN;
+    int rc = sim_alloc(g, sim, T, jam_tolerance, phys, mode);
+    if (rc) return rc;
+    DevBuf<u32> kin, vin;
+    if (T > 0) {
+        cudaStream_t st = ctx->stream;
+        const bool by_goal = mode == S4_ROOT_GOAL;
+        const int32_t *pr = by_goal ? goals : origins, *pt = by_goal ? origins : goals;
+        const int64_t nr = by_goal ? n_goals : n_origins, nt = by_goal ? n_origins : n_goals;
+        std::vector<int32_t> mr(pr, pr + nr), mt(pt, pt + nt);          // populations in the device's numbering
+        if (!g->rank.empty()) {
+            for (auto &x : mr) x = g->rank[(size_t)x];
+            for (auto &x : mt) x = g->rank[(size_t)x];
+        }
+        DevBuf<int32_t> d_r, d_t;
+        CU(d_r.alloc((size_t)nr));
+        CU(d_t.alloc((size_t)nt));
+        CU(kin.alloc((size_t)T));
+        CU(vin.alloc((size_t)T));
+        CU(cudaMemcpyAsync(d_r.p, mr.data(), (size_t)nr * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d_t.p, mt.data(), (size_t)nt * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        sample_trips_kernel<<<grid_for(T, 256, ctx), 256, 0, st>>>(T, (u64)seed, d_r.p, (u64)nr, by_goal ? 1 : 0, d_t.p, (u64)nt,
+                                                                   kin.p, vin.p);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(st));                                   // mr / mt / d_r / d_t go out of scope
+    }
+    if ((rc = sim_group(sim, kin, vin))) return rc;
+    guard.s = nullptr;
+    ++g->refs;
+    *out = sim;
+    return S4_OK;
+}
+
+// The simulation's trips in the caller's numbering, grouped by tree root (the order the device keeps them in).
+extern "C" int s4_sim_get_trips(s4_sim *sim, int32_t *origin_out, int32_t *goal_out)
+{
+    CHECK_ARG(sim && origin_out && goal_out, "s4_sim_get_trips: NULL argument");
+    s4_graph *g = sim->g;
+    s4_ctx *ctx = g->ctx;
+    CU(cudaSetDevice(ctx->device));
+    const int64_t T = sim->T, D = sim->D;
+    if (T == 0) return S4_OK;
+    std::vector<u32> troot((size_t)T);
+    std::vector<int32_t> ttarget((size_t)T), roots((size_t)D);
+    CU(cudaMemcpyAsync(troot.data(), sim->trip_root.p, (size_t)T * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(ttarget.data(), sim->trip_target.p, (size_t)T * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(roots.data(), sim->roots.p, (size_t)D * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    std::vector<int32_t> inv;                                           // device number -> caller's id
+    if (!g->rank.empty()) {
+        inv.resize((size_t)g->V);
+        for (int32_t i = 0; i < g->V; ++i) inv[(size_t)g->rank[(size_t)i]] = i;
+    }
+    int32_t *root_dst = sim->root_mode == S4_ROOT_GOAL ? goal_out : origin_out;
+    int32_t *target_dst = sim->root_mode == S4_ROOT_GOAL ? origin_out : goal_out;
+    for (int64_t t = 0; t < T; ++t) {
+        const int32_t r = roots[(size_t)troot[(size_t)t]], x = ttarget[(size_t)t];
+        root_dst[t] = inv.empty() ? r : inv[(size_t)r];
+        target_dst[t] = inv.empty() ? x : inv[(size_t)x];
+    }
     return S4_OK;
 }
 

@@ -841,6 +841,39 @@ __global__ void iota_kernel(int64_t n, u32 *out)
         out[i] = (u32)i;
 }
 
+// ---------------------------------------------------------------------------
+// Trip sampling on the device (tripgenerator.py:33-35 draws one origin and one goal per resident): trip t takes the
+// four words of Philox4x32-10 at counter (t, 0) under the key `seed` -- words 0,1 pick the origin, words 2,3 the
+// goal, index = floor(r64 * n / 2^64).  Counter based, so the list does not depend on the launch shape;
+// tripgenerator.philox_trip_indices is the same function in numpy.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const u32 hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const u32 hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
+__global__ void sample_trips_kernel(int64_t T, u64 seed, const int32_t *__restrict__ pop_root, u64 n_root, int root_words_hi,
+                                    const int32_t *__restrict__ pop_target, u64 n_target, u32 *__restrict__ root_out,
+                                    u32 *__restrict__ target_out)
+{
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < T; t += (int64_t)gridDim.x * blockDim.x) {
+        const uint4 r = philox4x32_10(make_uint4((u32)t, (u32)((u64)t >> 32), 0u, 0u), make_uint2((u32)seed, (u32)(seed >> 32)));
+        const u64 r_origin = ((u64)r.x << 32) | r.y, r_goal = ((u64)r.z << 32) | r.w;
+        // root_words_hi: the roots are the goals (words 2,3), the targets the origins (words 0,1)
+        const u64 rr = root_words_hi ? r_goal : r_origin, rt = root_words_hi ? r_origin : r_goal;
+        root_out[t] = (u32)pop_root[__umul64hi(rr, n_root)];
+        target_out[t] = (u32)pop_target[__umul64hi(rt, n_target)];
+    }
+}
+
 // trip grouping: after sorting trips by root, mark the first trip of every root
 __global__ void head_flag_kernel(int64_t T, const int32_t *__restrict__ sorted_root, u32 *__restrict__ flag)
 {

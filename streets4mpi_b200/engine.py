@@ -159,6 +159,34 @@ class DeviceSim(object):
         check(self.lib.s4_sim_roots(h, C.byref(n), C.byref(m)))
         self.n_roots, self.root_mode = n.value, m.value
 
+    @classmethod
+    def sampled(cls, graph, n_trips, origins, goals, seed, jam_tolerance, physics):
+        """A simulation whose trips are drawn on the device (s4_sim_create_sampled): one uniform origin and
+        one uniform goal per trip from the two populations (dense node ids)."""
+        self = cls.__new__(cls)
+        self.graph = graph
+        self.lib = graph.lib
+        origins = as_array(origins, np.int32)
+        goals = as_array(goals, np.int32)
+        h = C.c_void_p()
+        check(self.lib.s4_sim_create_sampled(graph._h, int(n_trips), len(origins), ptr(origins, C.c_int32), len(goals),
+                                             ptr(goals, C.c_int32), C.c_uint64(int(seed) & 0xFFFFFFFFFFFFFFFF),
+                                             float(jam_tolerance), C.byref(physics), C.byref(h)))
+        self._h = h
+        self.T = int(n_trips)
+        n = C.c_int64()
+        m = C.c_int()
+        check(self.lib.s4_sim_roots(h, C.byref(n), C.byref(m)))
+        self.n_roots, self.root_mode = n.value, m.value
+        return self
+
+    def get_trips(self):
+        """(origin int32[T], goal int32[T]) in dense node ids, grouped by tree root."""
+        o = np.empty(self.T, dtype=np.int32)
+        g = np.empty(self.T, dtype=np.int32)
+        check(self.lib.s4_sim_get_trips(self._h, ptr(o, C.c_int32), ptr(g, C.c_int32)))
+        return o, g
+
     def close(self):
         if getattr(self, "_h", None):
             self.lib.s4_sim_free(self._h)

@@ -16,7 +16,7 @@ import numpy as np
 
 from . import engine
 from .settings import device_settings, settings
-from .tripgenerator import TripTable
+from .tripgenerator import SampledTrips, TripTable
 
 
 def _to_array_I(a):
@@ -40,9 +40,21 @@ class Simulation(object):
                 self._device.set_option(key, device_settings[key])
         flat = street_network.flat()
         self._graph = street_network.device_graph(self._device)
-        table = trips if isinstance(trips, TripTable) else TripTable.from_dict(trips)
-        self._sim = engine.DeviceSim(self._graph, flat.dense(table.origins), flat.dense(table.goals),
-                                     float(jam_tolerance), engine.make_physics(settings))
+        if isinstance(trips, SampledTrips):
+            # drawn on the device: only the two populations cross PCIe
+            self._sim = engine.DeviceSim.sampled(self._graph, trips.number_of_trips, flat.dense(trips.origins),
+                                                 flat.dense(trips.goals), trips.seed, float(jam_tolerance),
+                                                 engine.make_physics(settings))
+            ids = flat.node_ids
+
+            def fetch(sim=self._sim):
+                o, g = sim.get_trips()
+                return ids[o], ids[g]
+            trips._fetch = fetch
+        else:
+            table = trips if isinstance(trips, TripTable) else TripTable.from_dict(trips)
+            self._sim = engine.DeviceSim(self._graph, flat.dense(table.origins), flat.dense(table.goals),
+                                         float(jam_tolerance), engine.make_physics(settings))
         if not np.array_equal(flat.max_speed, flat.max_speed_insertion):
             self._sim.set_max_speed(flat.max_speed, flat.max_speed_insertion)
         self._speed_version = street_network._speed_version

@@ -72,7 +72,78 @@ class TripTable(object):
         return TripTable(np.array(o, dtype=np.int64), np.array(g, dtype=np.int64))
 
 
+def philox_trip_indices(n_trips, n_origins, n_goals, seed):
+    """The draws of the device's trip sampler (csrc/s4_kernels.cuh sample_trips_kernel) in numpy: trip t takes the
+    four words of Philox4x32-10 at counter (t, 0, 0, 0) under key (seed & 0xffffffff, seed >> 32); words 0,1 pick
+    the origin, words 2,3 the goal, index = floor(r64 * n / 2**64).  Returns (origin_index, goal_index)."""
+    t = np.arange(n_trips, dtype=np.uint64)
+    c = [t & np.uint64(0xFFFFFFFF), t >> np.uint64(32), np.zeros(n_trips, np.uint64), np.zeros(n_trips, np.uint64)]
+    k0, k1 = int(seed) & 0xFFFFFFFF, (int(seed) >> 32) & 0xFFFFFFFF
+    m32 = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0 = np.uint64(0xD2511F53) * c[0]
+        p1 = np.uint64(0xCD9E8D57) * c[2]
+        c = [(p1 >> np.uint64(32)) ^ c[1] ^ np.uint64(k0), p1 & m32, (p0 >> np.uint64(32)) ^ c[3] ^ np.uint64(k1), p0 & m32]
+        k0 = (k0 + 0x9E3779B9) & 0xFFFFFFFF
+        k1 = (k1 + 0xBB67AE85) & 0xFFFFFFFF
+
+    def scale(hi, lo, n):                       # floor(((hi << 32) | lo) * n / 2**64) without 128-bit integers
+        n = np.uint64(n)
+        low = (lo * n) >> np.uint64(32)         # lo, hi < 2**32 and n < 2**31: every product fits in 64 bits
+        return ((hi * n + low) >> np.uint64(32)).astype(np.int64)
+    return scale(c[0], c[1], n_origins), scale(c[2], c[3], n_goals)
+
+
+class SampledTrips(object):
+    """Trips that are drawn on the device when the Simulation is built (TripGenerator.sample_trips_on_device):
+    only the two populations travel to the GPU.  ``table()`` gives the dict-like view (fetched back once)."""
+
+    def __init__(self, number_of_residents, potential_origins, potential_goals, seed):
+        self.number_of_trips = int(number_of_residents)
+        self.origins = np.asarray(sorted(potential_origins) if not isinstance(potential_origins, np.ndarray) else potential_origins)
+        self.goals = np.asarray(sorted(potential_goals) if not isinstance(potential_goals, np.ndarray) else potential_goals)
+        if self.number_of_trips > 0 and (len(self.origins) == 0 or len(self.goals) == 0):
+            raise ValueError("Sample larger than population or is negative")     # what random.sample raised
+        self.seed = int(seed)
+        self._table = None
+        self._fetch = None                       # set by Simulation: () -> (origins, goals) as original node ids
+
+    def host_table(self):
+        """The same trips computed on the host (numpy Philox): what the device draws."""
+        io, ig = philox_trip_indices(self.number_of_trips, len(self.origins), len(self.goals), self.seed)
+        return TripTable(self.origins[io], self.goals[ig])
+
+    def table(self):
+        if self._table is None:
+            self._table = TripTable(*self._fetch()) if self._fetch else self.host_table()
+        return self._table
+
+    def keys(self):
+        return self.table().keys()
+
+    def items(self):
+        return self.table().items()
+
+    def __getitem__(self, origin):
+        return self.table()[origin]
+
+    def __contains__(self, origin):
+        return origin in self.table()
+
+    def __iter__(self):
+        return iter(self.table())
+
+    def __len__(self):
+        return len(self.table())
+
+
 class TripGenerator(object):
+
+    def sample_trips_on_device(self, number_of_residents, potential_origins, potential_goals, seed):
+        """Like generate_trips (one uniform origin and one uniform goal per resident), but drawn by the GPU when
+        the Simulation is created: nothing of size number_of_residents is built on the host."""
+        return SampledTrips(number_of_residents, potential_origins, potential_goals, seed)
+
 
     def generate_trips(self, number_of_residents, potential_origins, potential_goals):
         # Python >= 3.11 no longer samples from sets; freeze them in sorted order

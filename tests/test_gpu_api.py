@@ -212,3 +212,54 @@ def test_visualization_speed_modes(tmp_path):
             assert len(vals) == net.street_index and 0.0 < max(vals) <= 1.0
     finally:
         os.chdir(cwd)
+
+
+def test_trips_sampled_on_the_device():
+    from streets4mpi_b200 import engine as _engine
+    from streets4mpi_b200.settings import settings as _settings
+    dev, phys = _engine.default_device(), _engine.make_physics(_settings)
+    _check_trips_sampled_on_the_device(dev, phys)
+
+
+def _check_trips_sampled_on_the_device(dev, phys):
+    """s4_sim_create_sampled: the device's Philox draws equal the numpy mirror trip for trip, both root modes; a day
+    on those trips is bit-equal to the oracle's; the Simulation / SampledTrips wrapper gives the dict view."""
+    from oracle import ctwin
+    from streets4mpi_b200 import Simulation, TripGenerator, engine, synth, tripgenerator
+    arr = synth.grid_arrays(40, 45, seed=8)
+    net = synth.network_from(arr)
+    flat = net.flat()
+    cats = synth.node_categories(arr["node_ids"], seed=8, goal_fraction=0.03)
+    origins, goals = np.sort(arr["node_ids"][::3]), cats["goals"]
+    g = engine.DeviceGraph(dev, flat.V, flat.u, flat.v, flat.length, flat.max_speed, node_rank=flat.locality_rank())
+    T, seed = 5000, 3756917 + 37
+    io, ig = tripgenerator.philox_trip_indices(T, len(origins), len(goals), seed)
+    want = sorted(zip(flat.dense(origins)[io].tolist(), flat.dense(goals)[ig].tolist()))
+    old = dev.get_option("root_mode")
+    try:
+        for mode in (0, 1, 2):
+            dev.set_option("root_mode", mode)
+            sim = engine.DeviceSim.sampled(g, T, flat.dense(origins), flat.dense(goals), seed, 0.3, phys)
+            o, gl = sim.get_trips()
+            assert sorted(zip(o.tolist(), gl.tolist())) == want, mode
+            if mode == 2:
+                assert sim.root_mode == 1                                    # fewer goals than origins
+            sim.step()
+            csr = ctwin.Csr(flat.V, flat.u, flat.v)
+            w = ctwin.weights(flat.length, flat.max_speed, np.zeros(flat.S, dtype=np.uint32), 0.3)
+            load, cnt = ctwin.day(csr, w, o, gl, nthreads=4)
+            assert cnt["tied_trips"] == 0 and np.array_equal(sim.get_load(), load), mode
+            sim.close()
+    finally:
+        dev.set_option("root_mode", old)
+    g.close()
+    st = TripGenerator().sample_trips_on_device(T, origins, goals, seed)
+    s2 = Simulation(net, st, 0.3, lambda *a: None, device=dev)
+    table = st.table()
+    host = st.host_table()
+    assert sorted(zip(table.origins.tolist(), table.goals.tolist())) == sorted(zip(host.origins.tolist(), host.goals.tolist()))
+    some = table.keys()[0]
+    assert some in st and len(st[some]) >= 1 and len(st) == len(table.keys())
+    s2.step()
+    assert int(np.frombuffer(s2.traffic_load, dtype=np.uint32).astype(np.int64).sum()) == s2.counters()["hops"]
+

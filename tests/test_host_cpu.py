@@ -187,6 +187,25 @@ def test_synthetic_generators():
     assert len(synth.parse_spec("synthetic:ladder:6x7")["node_ids"]) == 42
 
 
+def test_philox_trip_indices_known_answers():
+    """The host mirror of the device's trip sampler: Philox4x32-10 known answers (Random123 kat_vectors: counter 0 / key 0
+    -> 6627e8d5 e169c58d bc57ac4c 9b00dbd8; all ones -> 408f276d 41c83b0e a20bc7c6 6d5451fd) and uniform indices."""
+    from streets4mpi_b200 import tripgenerator as tg
+    # counter (t, 0, 0, 0) with t = 0 and key (0, 0): index = floor(r64 * n / 2^64) with n = 2^31 - 1 exposes the high bits
+    io, ig = tg.philox_trip_indices(1, 2 ** 31 - 1, 2 ** 31 - 1, 0)
+    r_o, r_g = (0x6627e8d5 << 32) | 0xe169c58d, (0xbc57ac4c << 32) | 0x9b00dbd8
+    assert int(io[0]) == (r_o * (2 ** 31 - 1)) >> 64 and int(ig[0]) == (r_g * (2 ** 31 - 1)) >> 64
+    io, ig = tg.philox_trip_indices(200000, 37, 11, 3756917)
+    assert io.min() == 0 and io.max() == 36 and ig.min() == 0 and ig.max() == 10
+    counts = np.bincount(io, minlength=37)
+    assert abs(counts - 200000 / 37).max() < 6 * np.sqrt(200000 / 37)         # uniform within 6 sigma
+    st = tg.TripGenerator().sample_trips_on_device(1000, [5, 9, 2], {7, 8}, seed=42)
+    t = st.host_table()
+    assert t.number_of_trips == 1000 and set(t.origins.tolist()) <= {2, 5, 9} and set(t.goals.tolist()) <= {7, 8}
+    with pytest.raises(ValueError):
+        tg.TripGenerator().sample_trips_on_device(10, [], [1], seed=1)
+
+
 def test_rank_seeding_known_answers():
     """streets4mpi.py:50-51,78: CPython's Mersenne Twister is the same in Py2 and Py3."""
     from streets4mpi_b200 import distributed
