@@ -8,6 +8,8 @@ here they are binary.  Pickles use protocol 2 so a Python-2 reader can load them
 """
 import array
 import pickle
+import queue
+import threading
 import zlib
 
 
@@ -39,3 +41,65 @@ def persist_read(filename, compressed=True, is_array=False):
         result.frombytes(zlib.decompress(blob))
         return result
     return persist_deserialize(blob, compressed)
+
+
+class AsyncWriter(object):
+    """persist_write off the critical path of the day loop (streets4mpi.py:89-90,102-104 wrote synchronously; at one
+    simulated day per second the zlib pass over 8-240 MB of counters would be a visible share of it).
+
+    ``write()`` snapshots the data in the caller -- a copy of the array bytes, or the pickle of the object as it is
+    now -- and a worker thread compresses (zlib releases the GIL) and writes the files in submission order, byte for
+    byte what persist_write produces.  ``close()`` waits for the queue to drain and re-raises the first error."""
+
+    def __init__(self, max_pending=4):
+        self._q = queue.Queue(max_pending)
+        self._error = None
+        self._thread = threading.Thread(target=self._run, name="s4mpi-persist", daemon=True)
+        self._thread.start()
+
+    def _run(self):
+        while True:
+            item = self._q.get()
+            try:
+                if item is None:
+                    return
+                filename, blob, compress = item
+                if self._error is None:
+                    with open(filename, "wb") as f:
+                        f.write(zlib.compress(blob) if compress else blob)
+            except Exception as e:                      # reported by close() / the next write()
+                self._error = e
+            finally:
+                self._q.task_done()
+
+    def write(self, filename, data, compress=True, is_array=False):
+        if self._error is not None:
+            raise self._error
+        if is_array:
+            blob = data.tobytes() if isinstance(data, array.array) else array.array("I", data).tobytes()
+            compress = True                             # persist_write always compresses arrays
+        else:
+            blob = pickle.dumps(data, protocol=2)
+        self._q.put((filename, blob, compress))
+
+    def flush(self):
+        self._q.join()
+        if self._error is not None:
+            raise self._error
+
+    def close(self):
+        if self._thread is not None:
+            self._q.put(None)
+            self._thread.join()
+            self._thread = None
+        if self._error is not None:
+            err, self._error = self._error, None
+            raise err
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+

@@ -13,7 +13,7 @@ import random
 from datetime import datetime
 
 from . import distributed, synth
-from .persistence import persist_write
+from .persistence import AsyncWriter
 from .settings import settings
 from .simulation import Simulation
 from .tripgenerator import TripGenerator
@@ -46,9 +46,11 @@ class Streets4MPI(object):
             residential = data.connected_residential_nodes
             goals = data.connected_commercial_nodes | data.connected_industrial_nodes       # :74
 
-        if self.process_rank == 0 and settings["persist_traffic_load"]:
+        # same files as the reference, compressed and written by a worker thread while the next day runs
+        writer = AsyncWriter() if self.process_rank == 0 and settings["persist_traffic_load"] else None
+        if writer:
             self.log_indent("Saving street network to disk...")
-            persist_write("street_network_1.s4mpi", street_network)                         # :59-61
+            writer.write("street_network_1.s4mpi", street_network)                          # :59-61
 
         self.log("Generating trips...")
         number_of_residents = distributed.residents_of_rank(settings["number_of_residents"], number_of_processes)
@@ -65,8 +67,8 @@ class Streets4MPI(object):
             if step > 0 and step % settings["steps_between_street_construction"] == 0:      # :86
                 self.log_indent("Road construction taking place...")
                 simulation.road_construction()
-                if self.process_rank == 0 and settings["persist_traffic_load"]:
-                    persist_write("street_network_" + str(step + 1) + ".s4mpi", simulation.street_network)
+                if writer:
+                    writer.write("street_network_" + str(step + 1) + ".s4mpi", simulation.street_network)
 
             self.log("Running simulation step", step + 1, "of", str(settings["max_simulation_steps"]) + "...")
             simulation.step()
@@ -74,10 +76,12 @@ class Streets4MPI(object):
             self.log("Exchanging traffic load data between nodes...")
             simulation.exchange()                                                           # :97-100, on the device
 
-            if self.process_rank == 0 and settings["persist_traffic_load"]:
+            if writer:
                 self.log_indent("Saving traffic load to disk...")
-                persist_write("traffic_load_" + str(step + 1) + ".s4mpi", simulation.traffic_load, is_array=True)
+                writer.write("traffic_load_" + str(step + 1) + ".s4mpi", simulation.traffic_load, is_array=True)
 
+        if writer:
+            writer.close()
         self.log("Done!")
 
     def log(self, *output):

@@ -187,6 +187,30 @@ def test_synthetic_generators():
     assert len(synth.parse_spec("synthetic:ladder:6x7")["node_ids"]) == 42
 
 
+def test_async_writer_matches_persist_write(tmp_path):
+    """persistence.AsyncWriter: same bytes as persist_write, snapshot at submission, errors surface at close()."""
+    from array import array
+    from streets4mpi_b200 import persistence
+    load = array("I", range(5000))
+    obj = {"a": [1, 2, 3], "b": "street"}
+    persistence.persist_write(str(tmp_path / "ref_load.s4mpi"), load, is_array=True)
+    persistence.persist_write(str(tmp_path / "ref_obj.s4mpi"), obj)
+    with persistence.AsyncWriter(max_pending=2) as w:
+        w.write(str(tmp_path / "load.s4mpi"), load, is_array=True)
+        load[0] = 77                                                   # later changes must not reach the file
+        w.write(str(tmp_path / "obj.s4mpi"), obj)
+        obj["a"].append(4)
+        w.write(str(tmp_path / "load_np.s4mpi"), np.arange(10, dtype=np.uint32), is_array=True)
+        w.flush()
+    assert (tmp_path / "load.s4mpi").read_bytes() == (tmp_path / "ref_load.s4mpi").read_bytes()
+    assert (tmp_path / "obj.s4mpi").read_bytes() == (tmp_path / "ref_obj.s4mpi").read_bytes()
+    assert persistence.persist_read(str(tmp_path / "load_np.s4mpi"), is_array=True).tolist() == list(range(10))
+    w = persistence.AsyncWriter()
+    w.write(str(tmp_path / "no_such_dir" / "x.s4mpi"), load, is_array=True)
+    with pytest.raises(OSError):
+        w.close()
+
+
 def test_philox_trip_indices_known_answers():
     """The host mirror of the device's trip sampler: Philox4x32-10 known answers (Random123 kat_vectors: counter 0 / key 0
     -> 6627e8d5 e169c58d bc57ac4c 9b00dbd8; all ones -> 408f276d 41c83b0e a20bc7c6 6d5451fd) and uniform indices."""
