@@ -33,6 +33,10 @@ device_settings = {
     # Reproduce python-graph's per-orientation attribute lists: a street inserted as (u, v) with u > v
     # never shows a changed speed limit to the weight loop (streetnetwork.py:79-82 vs :113-125).
     "orientation_aliasing": True,
+    # Draw the trips on the GPU (Philox sampler, seed = random_seed + 37 * rank) instead of with random.sample on the
+    # host: same distribution (one uniform origin, one uniform goal per resident), a different but reproducible
+    # list -- trip lists are run inputs -- and no Python loop over the residents.  For 10^7..10^8-trip runs.
+    "sample_trips_on_device": False,
     # SSSP kernel tunables (None = library default), see include/s4mpi.h s4_ctx_set_option
     "delta_factor": None,
     "block_threads": None,

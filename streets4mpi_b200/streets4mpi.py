@@ -14,7 +14,7 @@ from datetime import datetime
 
 from . import distributed, synth
 from .persistence import AsyncWriter
-from .settings import settings
+from .settings import device_settings, settings
 from .simulation import Simulation
 from .tripgenerator import TripGenerator
 
@@ -55,7 +55,11 @@ class Streets4MPI(object):
         self.log("Generating trips...")
         number_of_residents = distributed.residents_of_rank(settings["number_of_residents"], number_of_processes)
         potential_origins = residential if settings["use_residential_origins"] else street_network.get_nodes()
-        trips = TripGenerator().generate_trips(number_of_residents, potential_origins, goals)   # :75
+        if device_settings.get("sample_trips_on_device"):
+            trips = TripGenerator().sample_trips_on_device(number_of_residents, potential_origins, goals,
+                                                           distributed.rank_seed(settings["random_seed"], self.process_rank))
+        else:
+            trips = TripGenerator().generate_trips(number_of_residents, potential_origins, goals)   # :75
 
         jam_tolerance = random.random()                                                     # :78
         self.log("Setting traffic jam tolerance to", str(round(jam_tolerance, 2)) + "...")

@@ -137,6 +137,34 @@ def test_streets4mpi_driver_end_to_end(tmp_path):
         settings.update(old)
 
 
+def test_streets4mpi_driver_with_device_trip_sampling(tmp_path):
+    """device_settings["sample_trips_on_device"]: the driver's trips come from the GPU's Philox sampler (seed =
+    random_seed + 37 * rank); the day loop, persistence and conservation are unchanged."""
+    from streets4mpi_b200 import persistence, tripgenerator
+    from streets4mpi_b200.settings import device_settings, settings
+    from streets4mpi_b200.streets4mpi import Streets4MPI
+    old, old_dev = dict(settings), dict(device_settings)
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        settings.update({"osm_file": "synthetic:grid:30x20:4", "logging": None, "max_simulation_steps": 3,
+                         "number_of_residents": 2000, "steps_between_street_construction": 10})
+        device_settings["sample_trips_on_device"] = True
+        app = Streets4MPI()
+        trips = app.simulation.trips
+        assert isinstance(trips, tripgenerator.SampledTrips) and trips.number_of_trips == 2000 and trips.seed == 3756917
+        table, host = trips.table(), trips.host_table()
+        assert sorted(zip(table.origins.tolist(), table.goals.tolist())) == sorted(zip(host.origins.tolist(), host.goals.tolist()))
+        day3 = persistence.persist_read("traffic_load_3.s4mpi", is_array=True)
+        assert list(day3) == list(app.simulation.traffic_load) and sum(day3) > 0
+    finally:
+        os.chdir(cwd)
+        settings.clear()
+        settings.update(old)
+        device_settings.clear()
+        device_settings.update(old_dev)
+
+
 @pytest.mark.parametrize("residents,every", [(100, 10), (3000, 4)])
 def test_streets4mpi_on_osm_file_matches_port(tmp_path, residents, every):
     """BASELINE configs[0]/[1] stand-in: the zero-argument driver on an OSM XML file (the reference's
