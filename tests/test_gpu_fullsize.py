@@ -81,3 +81,42 @@ def test_fullsize_day_properties(cfg3):
     sim.step()
     assert cnt["tied_trips"] == 0 and np.array_equal(sim.get_load(), want)
     sim.close()
+
+
+def test_road_like_graph_at_scale():
+    """cfg4 / cfg5 shape at 1.44 M nodes (street chains joined by sparse rungs, mean degree 2.4: thin waves, narrow CTAs,
+    adaptive bucket width, overlapped buckets): two whole trees bit-equal to the oracle's, and a day of 5 k trips from
+    144 residential origins bit-equal to the oracle's load."""
+    from oracle import ctwin
+    from streets4mpi_b200 import engine, synth
+    from streets4mpi_b200.settings import settings
+    dev = engine.default_device()
+    phys = engine.make_physics(settings)
+    arr = synth.ladder_arrays(1200, 1200, seed=2)
+    flat = synth.network_from(arr).flat()
+    g = engine.DeviceGraph(dev, flat.V, flat.u, flat.v, flat.length, flat.max_speed, node_rank=flat.locality_rank())
+    csr = ctwin.Csr(flat.V, flat.u, flat.v)
+    rng = np.random.default_rng(5)
+    w = rng.uniform(0.1, 13.0, size=flat.S)
+    for src in (0, flat.V // 2 + 77):
+        dist, pred = g.sssp(w, src)
+        d0, p0, tied = ctwin.sssp(csr, w, src)
+        assert np.array_equal(dist.view(np.uint64), d0.view(np.uint64))
+        assert np.array_equal(pred, p0)
+    cats = synth.node_categories(arr["node_ids"], seed=2, goal_fraction=0.02, residential_fraction=0.0001)
+    o, gl = synth.trip_arrays(5000, cats["residential"], cats["goals"], seed=9)
+    old = dev.get_option("root_mode")
+    try:
+        dev.set_option("root_mode", 0)                        # 144 residential origins -> 144 trees
+        sim = engine.DeviceSim(g, flat.dense(o), flat.dense(gl), 0.4, phys)
+        sim.step()
+        c = sim.counters()
+        w0 = ctwin.weights(flat.length, flat.max_speed, np.zeros(flat.S, dtype=np.uint32), 0.4)
+        want, cnt = ctwin.day(csr, w0, flat.dense(o), flat.dense(gl), nthreads=16)
+        assert cnt["tied_trips"] == 0 and c["fallback_sweeps"] == 0 and c["trips_unreachable"] == 0
+        assert np.array_equal(sim.get_load(), want)
+        sim.close()
+    finally:
+        dev.set_option("root_mode", old)
+    g.close()
+
