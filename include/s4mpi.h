@@ -135,6 +135,9 @@ int s4_graph_upload(s4_ctx *ctx, int32_t V, int64_t S, const int32_t *u, const i
                     const double *length, const int32_t *max_speed, const int32_t *node_rank, s4_graph **out);
 int s4_graph_free(s4_graph *g);
 int s4_graph_dims(s4_graph *g, int32_t *V, int64_t *S, int64_t *A);
+/* Diagnostics (option "group_log" = 1): 4 words per group of trees of the last s4_sim_step on this graph --
+ * {SM cycles >> 10, relaxation rounds, frontier entries popped, bucket advances}.  out may be NULL to size the buffer. */
+int s4_graph_group_log(s4_graph *g, uint32_t *out, int64_t cap_words, int64_t *n_words);
 /* StreetNetwork.calculate_shortest_paths (streetnetwork.py:108-109) with
  * explicit per-street weights (the network's current driving times,
  * streetnetwork.py:60-61).  dist_out[V] (+inf = unreachable), pred_out[V]

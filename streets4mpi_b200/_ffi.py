@@ -57,6 +57,7 @@ SIGNATURES = {
     "s4_graph_upload": (C.c_int, [_vp, C.c_int32, C.c_int64, _i32p, _i32p, _f64p, _i32p, _i32p, C.POINTER(_vp)]),
     "s4_graph_free": (C.c_int, [_vp]),
     "s4_graph_dims": (C.c_int, [_vp, C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "s4_graph_group_log": (C.c_int, [_vp, _u32p, C.c_int64, C.POINTER(C.c_int64)]),
     "s4_graph_sssp": (C.c_int, [_vp, _f64p, C.c_int32, _f64p, _i32p]),
     "s4_sim_create": (C.c_int, [_vp, C.c_int64, _i32p, _i32p, C.c_double, C.POINTER(Physics), C.POINTER(_vp)]),
     "s4_sim_free": (C.c_int, [_vp]),

@@ -4,6 +4,7 @@
 // the CUDA path or reports an error.
 #include "../../include/s4mpi.h"
 #include "s4_kernels.cuh"
+#include "s4_sssp_group.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -51,7 +52,7 @@ static int fail(int code, const char *fmt, ...)
 // objects
 // ---------------------------------------------------------------------------
 struct Options {
-    double delta_factor = 3.0;
+    double delta_factor = 1.5;
     int block_threads = 0;          // 0 = from the graph (mean frontier width ~ V / hop depth)
     int ctas_per_sm = 0;            // 0 = as many CTAs as keep 1024 threads per SM
     int near_smem_entries = 0;      // 0 = 6 entries per thread
@@ -67,7 +68,24 @@ struct Options {
                                     // (0 = only when the near queue is empty); measured on cfg3 and a planar graph
     int preread = 2;                // 1: filtering read, then returning atomicMin;
                                     // 2: filtering read decides the push, minimum sent as RED (no wait)
+    int group_lanes = 8;            // lanes that expand one node for a whole group of trees (4 | 8); 0: one tree per CTA
+    int group_words = 2;            // distance words per lane (1 | 2): trees per group = group_lanes * group_words - 1
+    double lag_factor = 1.0;        // source-batched kernel: hold a node back by this multiple of the root-to-root distance
+    int group_log = 0;              // diagnostics: keep per-group cycles / rounds / entries of the last day (s4_graph_group_log)
+    int min_batches = 4;            // a day is cut into at least this many (SSSP launch -> walk) batches when lanes = 2
 };
+
+// how the trees of a launch are laid out in the distance pool
+struct Layout {
+    int K = 1;       // trees per slot
+    int RW = 1;      // words per node row
+};
+static Layout layout_of(const Options &o)
+{
+    Layout l;
+    if (o.group_lanes > 0) { l.RW = o.group_lanes * o.group_words; l.K = l.RW - 1; }
+    return l;
+}
 
 // Lifetime: handles are reference counted (sim -> graph -> ctx), so the host may
 // release them in any order (Python finalisers run in arbitrary order).
@@ -119,6 +137,8 @@ struct s4_graph {
     DevBuf<u32> orig;          // device number -> caller's dense id (empty = identity numbering)
     std::vector<int32_t> rank; // caller's dense id -> device number (empty = identity)
     std::vector<int32_t> max_speed0;   // host copy of the uploaded limits
+    std::vector<u32> gorder_h, ginv_h;  // grouping order of tree roots: device number -> position / position -> device number
+    DevBuf<u32> gorder, ginv;
     // connected components (host): algorithmic arcs / nodes of a tree rooted at r
     std::vector<int32_t> comp_of;
     std::vector<int64_t> comp_arcs, comp_nodes;
@@ -133,6 +153,8 @@ struct s4_graph {
     bool ws_auto = false;      // workspace sized by the library (not by the "queue_entries" option)
     u32 near_gcap = 0, far_cap = 0;
     DevBuf<u32> work_counters;
+    DevBuf<u32> glog;          // diagnostics of the source-batched kernel: 4 words per group of the last day
+    int64_t glog_groups = 0;
     // single-source API scratch
     DevBuf<Arc> arcs_tmp, ell_tmp;
     DevBuf<double> w_tmp;
@@ -262,7 +284,9 @@ static void option_slot(Options &o, const char *key, int *kind, void **raw)
         {"root_mode", 1, &o.root_mode},             {"walk_tile", 1, &o.walk_tile},
         {"preread", 1, &o.preread},                 {"lanes", 1, &o.lanes},
         {"adaptive_delta", 1, &o.adaptive_delta},   {"early_advance", 1, &o.early_advance},
-        {"walk_ell", 1, &o.walk_ell},
+        {"walk_ell", 1, &o.walk_ell},                {"group_lanes", 1, &o.group_lanes},
+        {"group_words", 1, &o.group_words},         {"lag_factor", 0, &o.lag_factor},
+        {"min_batches", 1, &o.min_batches},         {"group_log", 1, &o.group_log},
     };
     for (auto &it : items)
         if (strcmp(it.k, key) == 0) { *kind = it.kind; *raw = it.p; return; }
@@ -289,7 +313,9 @@ extern "C" int s4_ctx_set_option(s4_ctx *ctx, const char *key, double value)
               t.batch_roots >= 0 && t.pool_bytes >= 0.0 && t.root_mode >= 0 && t.root_mode <= 2 &&
               (t.walk_tile == 0 || t.walk_tile == 4 || t.walk_tile == 8 || t.walk_tile == 16 || t.walk_tile == 32) &&
               (t.preread == 1 || t.preread == 2) && (t.lanes == 1 || t.lanes == 2) &&
-              t.early_advance >= 0 && t.early_advance <= 64 && (t.walk_ell == 0 || t.walk_ell == 1);
+              t.early_advance >= 0 && t.early_advance <= 64 && (t.walk_ell == 0 || t.walk_ell == 1) &&
+              (t.group_lanes == 0 || t.group_lanes == 4 || t.group_lanes == 8) && (t.group_words == 1 || t.group_words == 2) &&
+              t.lag_factor >= 0.0 && t.lag_factor <= 64.0 && t.min_batches >= 1 && t.min_batches <= 64;
     if (!ok) return fail(S4_ERR_ARG, "option '%s': value %g out of range", key, value);
     ctx->opt = trial;
     return S4_OK;
@@ -467,6 +493,59 @@ extern "C" int s4_graph_upload(s4_ctx *ctx, int32_t V, int64_t S, const int32_t 
         int64_t wide = 0;
         for (int32_t i = 0; i < V; ++i) wide += (row_ptr[(size_t)i + 1] - row_ptr[(size_t)i]) > 4u;
         g->auto_walk_tile = wide * 2 > (int64_t)V ? 16 : 8;      // 8 lanes cover a road node's arcs in one step (measured: 4 is slower)
+
+        // Grouping order of tree roots for the source-batched SSSP kernel: the trees of one group should be close
+        // in the GRAPH metric (their waves then pass every node together).  Coordinates may be missing or
+        // misleading (a river, a motorway without exits), so the order comes from the graph itself: four landmark
+        // BFS sweeps (a, b = the two ends found above; c = the node farthest from both; d = the node farthest
+        // from c) embed every node at (hops(a) - hops(b), hops(c) - hops(d)) -- on a lattice that is its position
+        // rotated by 45 degrees -- and the nodes are ordered along a Hilbert curve over that plane.
+        {
+            std::vector<int32_t> da(level);                          // level = hops from far1 (a)
+            int32_t dummy = 0;
+            bfs(far2, &dummy, &reached);
+            std::vector<int32_t> db(level);
+            int32_t c_node = far1;
+            int32_t best_min = -1;
+            for (int32_t i = 0; i < V; ++i) {
+                if (da[(size_t)i] < 0 || db[(size_t)i] < 0) continue;
+                const int32_t m = std::min(da[(size_t)i], db[(size_t)i]);
+                if (m > best_min) { best_min = m; c_node = i; }
+            }
+            int32_t d_node = c_node;
+            bfs(c_node, &d_node, &reached);
+            std::vector<int32_t> dc(level);
+            bfs(d_node, &dummy, &reached);
+            const std::vector<int32_t> &dd = level;
+            const int64_t span1 = 2 * (int64_t)depth + 1, span2 = 2 * (int64_t)std::max<int32_t>(1, dc[(size_t)d_node]) + 1;
+            std::vector<std::pair<uint64_t, int32_t>> keyed((size_t)V);
+            for (int32_t i = 0; i < V; ++i) {
+                uint64_t x = 0, y = 0;
+                if (da[(size_t)i] >= 0 && db[(size_t)i] >= 0 && dc[(size_t)i] >= 0 && dd[(size_t)i] >= 0) {
+                    const int64_t u1 = (int64_t)da[(size_t)i] - db[(size_t)i] + depth;                       // 0 .. 2 * depth
+                    const int64_t u2 = (int64_t)dc[(size_t)i] - dd[(size_t)i] + (span2 - 1) / 2;
+                    x = (uint64_t)std::min<int64_t>(65535, std::max<int64_t>(0, u1 * 65535 / std::max<int64_t>(1, span1 - 1)));
+                    y = (uint64_t)std::min<int64_t>(65535, std::max<int64_t>(0, u2 * 65535 / std::max<int64_t>(1, span2 - 1)));
+                }
+                uint64_t key = 0;                                    // Hilbert index of (x, y) on the 65536^2 lattice
+                for (uint64_t sft = 32768; sft > 0; sft >>= 1) {
+                    const uint64_t rx = (x & sft) ? 1 : 0, ry = (y & sft) ? 1 : 0;
+                    key += sft * sft * ((3 * rx) ^ ry);
+                    if (ry == 0) {                                   // rotate the quadrant (bits above sft are not read again)
+                        if (rx == 1) { x = 65535 - x; y = 65535 - y; }
+                        std::swap(x, y);
+                    }
+                }
+                keyed[(size_t)i] = std::make_pair(key, i);
+            }
+            std::sort(keyed.begin(), keyed.end());
+            g->gorder_h.resize((size_t)V);
+            g->ginv_h.resize((size_t)V);
+            for (int32_t pos = 0; pos < V; ++pos) {
+                g->ginv_h[(size_t)pos] = (u32)keyed[(size_t)pos].second;
+                g->gorder_h[(size_t)keyed[(size_t)pos].second] = (u32)pos;
+            }
+        }
     }
     auto bail = [&](cudaError_t e, const char *what) {
         delete g;
@@ -478,6 +557,9 @@ extern "C" int s4_graph_upload(s4_ctx *ctx, int32_t V, int64_t S, const int32_t 
     if ((e = g->arc_cs.alloc((size_t)std::max<int64_t>(A, 1))) != cudaSuccess) return bail(e, "alloc arcs");
     if ((e = g->length.alloc((size_t)std::max<int64_t>(S, 1))) != cudaSuccess) return bail(e, "alloc length");
     if ((e = g->ell_cs.alloc((size_t)V * kEllWidth)) != cudaSuccess) return bail(e, "alloc ell");
+    if ((e = g->gorder.alloc((size_t)V)) != cudaSuccess || (e = g->ginv.alloc((size_t)V)) != cudaSuccess) return bail(e, "alloc grouping order");
+    if ((e = cudaMemcpyAsync(g->gorder.p, g->gorder_h.data(), (size_t)V * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) return bail(e, "copy grouping order");
+    if ((e = cudaMemcpyAsync(g->ginv.p, g->ginv_h.data(), (size_t)V * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) return bail(e, "copy grouping order");
     if (node_rank) {
         if ((e = g->orig.alloc((size_t)V)) != cudaSuccess) return bail(e, "alloc orig");
         if ((e = cudaMemcpyAsync(g->orig.p, orig_h.data(), (size_t)V * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) return bail(e, "copy orig");
@@ -508,6 +590,19 @@ extern "C" int s4_graph_free(s4_graph *g)
     return S4_OK;
 }
 
+extern "C" int s4_graph_group_log(s4_graph *g, uint32_t *out, int64_t cap_words, int64_t *n_words)
+{
+    CHECK_ARG(g && n_words, "s4_graph_group_log: NULL argument");
+    CU(cudaSetDevice(g->ctx->device));
+    CU(cudaDeviceSynchronize());
+    *n_words = g->glog_groups * 4;
+    if (out && g->glog_groups > 0) {
+        CHECK_ARG(cap_words >= *n_words, "s4_graph_group_log: buffer too small");
+        CU(cudaMemcpy(out, g->glog.p, (size_t)*n_words * sizeof(u32), cudaMemcpyDeviceToHost));
+    }
+    return S4_OK;
+}
+
 extern "C" int s4_graph_dims(s4_graph *g, int32_t *V, int64_t *S, int64_t *A)
 {
     CHECK_ARG(g, "s4_graph_dims: graph is NULL");
@@ -521,6 +616,7 @@ extern "C" int s4_graph_dims(s4_graph *g, int32_t *V, int64_t *S, int64_t *A)
 // SSSP launch plumbing
 // ---------------------------------------------------------------------------
 typedef void (*SsspKernel)(SsspParams);
+typedef void (*GroupKernel)(GroupParams);
 
 static SsspKernel pick_sssp(int block)
 {
@@ -535,12 +631,44 @@ static SsspKernel pick_sssp(int block)
     return nullptr;
 }
 
+template <int LP, int TL>
+static GroupKernel pick_group_block(int block)
+{
+    switch (block) {
+        case 32: return sssp_group_kernel<32, LP, TL>;
+        case 64: return sssp_group_kernel<64, LP, TL>;
+        case 128: return sssp_group_kernel<128, LP, TL>;
+        case 256: return sssp_group_kernel<256, LP, TL>;
+        case 512: return sssp_group_kernel<512, LP, TL>;
+        case 1024: return sssp_group_kernel<1024, LP, TL>;
+    }
+    return nullptr;
+}
+
+static GroupKernel pick_group(int block, int lanes, int words)
+{
+    if (lanes == 8 && words == 1) return pick_group_block<8, 1>(block);
+    if (lanes == 8 && words == 2) return pick_group_block<8, 2>(block);
+    if (lanes == 4 && words == 1) return pick_group_block<4, 1>(block);
+    if (lanes == 4 && words == 2) return pick_group_block<4, 2>(block);
+    return nullptr;
+}
+
 struct SsspLaunch {
-    SsspKernel fn = nullptr;
+    SsspKernel fn = nullptr;        // one tree per CTA ...
+    GroupKernel gfn = nullptr;      // ... or a group of trees per CTA
+    Layout lay;
     int block = 0, grid = 0;
     size_t smem = 0;
     u32 scap = 0;
+    const void *func() const { return gfn ? (const void *)gfn : (const void *)fn; }
 };
+
+// words of one slot of the distance pool (the rows of lay.K trees)
+static size_t slot_words(const s4_graph *g, const Layout &lay)
+{
+    return lay.RW == 1 ? (size_t)((g->V + 3) & ~3) : (size_t)g->V * (size_t)lay.RW;
+}
 
 // Device memory the scratch of a graph may take: the pool of per-tree distance arrays (55 % of what is free,
 // or the "pool_bytes" option if that is smaller) and the per-CTA frontier workspace (15 %).
@@ -561,33 +689,45 @@ static int scratch_budget(s4_graph *g, double *pool_budget, double *ws_budget)
 static int plan_sssp(s4_graph *g, SsspLaunch *L)
 {
     const Options &o = g->ctx->opt;
-    int block = o.block_threads ? o.block_threads : g->auto_block;
+    L->lay = layout_of(o);
+    const bool grouped = o.group_lanes > 0;
+    // CTA width from the graph's wave width (graph upload): a tree keeps about `auto_block` nodes in flight per
+    // relaxation round; the source-batched kernel spends group_lanes lanes on every node it expands
+    int block = o.block_threads ? o.block_threads : grouped ? std::min(1024, g->auto_block * o.group_lanes / 2) : g->auto_block;
+    block = std::max(block, 32);
     if (!o.block_threads) {
-        // narrow CTAs only pay off when that many trees fit in flight: each needs a distance slot (8 B x V)
+        // narrow CTAs only pay off when that many slots fit in flight
         double pool_budget = 0.0, ws_budget = 0.0;
         int rc = scratch_budget(g, &pool_budget, &ws_budget);
         if (rc) return rc;
-        const double per_slot = 8.0 * (double)g->V;
-        const int64_t slots = o.batch_roots > 0 ? o.batch_roots : (int64_t)(pool_budget / per_slot);
+        const double per_slot = 8.0 * (double)slot_words(g, L->lay);
+        const int64_t slots = o.batch_roots > 0 ? std::max<int64_t>(1, o.batch_roots / L->lay.K) : (int64_t)(pool_budget / per_slot);
         const int64_t per_lane = std::max<int64_t>(1, slots / 2);
         while (block < 1024 && (int64_t)g->ctx->prop.multiProcessorCount * std::min(32, 1024 / block) > per_lane) block *= 2;
     }
-    const int near_entries = o.near_smem_entries ? o.near_smem_entries : std::max(128, 6 * block);     // measured on cfg3
+    const int near_entries = o.near_smem_entries ? o.near_smem_entries : grouped ? std::max(256, 8 * block) : std::max(128, 6 * block);
     const int ctas = o.ctas_per_sm ? o.ctas_per_sm : std::min(32, std::max(1, 1024 / block));
-    L->fn = pick_sssp(block);
-    if (!L->fn) return fail(S4_ERR_ARG, "no SSSP kernel for block=%d", block);
+    if (grouped) {
+        L->gfn = pick_group(block, o.group_lanes, o.group_words);
+        L->fn = nullptr;
+        if (!L->gfn) return fail(S4_ERR_ARG, "no source-batched SSSP kernel for block=%d lanes=%d words=%d", block, o.group_lanes, o.group_words);
+    } else {
+        L->fn = pick_sssp(block);
+        L->gfn = nullptr;
+        if (!L->fn) return fail(S4_ERR_ARG, "no SSSP kernel for block=%d", block);
+    }
     L->block = block;
     L->scap = (u32)near_entries;
-    L->smem = (size_t)2 * L->scap * (sizeof(u64) + sizeof(u32));
-    CU(cudaFuncSetAttribute((const void *)L->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L->smem));
+    L->smem = grouped ? (size_t)2 * L->scap * sizeof(u32) : (size_t)2 * L->scap * (sizeof(u64) + sizeof(u32));
+    CU(cudaFuncSetAttribute(L->func(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L->smem));
     int occ = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)L->fn, L->block, L->smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, L->func(), L->block, L->smem));
     if (occ < 1) return fail(S4_ERR_ARG, "SSSP kernel does not fit on an SM (block=%d, smem=%zu)", L->block, L->smem);
     L->grid = g->ctx->prop.multiProcessorCount * std::min(occ, ctas);
     return S4_OK;
 }
 
-// pool + per-CTA queue workspace, sized from the options; slots_wanted caps the pool
+// pool + per-CTA queue workspace, sized from the options; slots_wanted (in slots of lay.K trees) caps the pool
 static int ensure_scratch(s4_graph *g, const SsspLaunch &L, int64_t slots_wanted)
 {
     const Options &o = g->ctx->opt;
@@ -595,13 +735,12 @@ static int ensure_scratch(s4_graph *g, const SsspLaunch &L, int64_t slots_wanted
     double pool_budget = 0.0, ws_budget = 0.0;
     int rc = scratch_budget(g, &pool_budget, &ws_budget);
     if (rc) return rc;
-    const int64_t by_mem = (int64_t)(pool_budget / (8.0 * (double)V));
-    int64_t slots = o.batch_roots > 0 ? std::min<int64_t>(o.batch_roots, by_mem) : by_mem;
+    const size_t sw = slot_words(g, L.lay);
+    const int64_t by_mem = (int64_t)(pool_budget / (8.0 * (double)sw));
+    int64_t slots = o.batch_roots > 0 ? std::min<int64_t>(std::max<int64_t>(1, o.batch_roots / L.lay.K), by_mem) : by_mem;
     slots = std::max<int64_t>(1, std::min(slots, slots_wanted));
-    if (slots > g->pool_slots || !g->pool.p) {
-        CU(g->pool.alloc((size_t)slots * (size_t)((V + 3) & ~(int64_t)3)));
-        g->pool_slots = slots;
-    }
+    if ((size_t)slots * sw > g->pool.n || !g->pool.p) CU(g->pool.alloc((size_t)slots * sw));
+    g->pool_slots = (int64_t)(g->pool.n / sw);
     // per-CTA spill / far-pile capacity: a quarter of the nodes for a 256-wide CTA, proportionally less for
     // the narrow CTAs used on thin-wave graphs (an overflow is survivable: Bellman-Ford safety net)
     int64_t q = o.queue_entries > 0 ? o.queue_entries
@@ -628,31 +767,64 @@ static int ensure_scratch(s4_graph *g, const SsspLaunch &L, int64_t slots_wanted
     return S4_OK;
 }
 
-static int launch_sssp(s4_graph *g, const SsspLaunch &L, const Arc *ell, const Arc *arcs, const int32_t *d_roots,
+// rows: the fixed-stride table the kernel expands from (ell for one tree per CTA, ellw for the source-batched kernel)
+static int launch_sssp(s4_graph *g, const SsspLaunch &L, const Arc *rows, const Arc *arcs, const int32_t *d_roots,
                        int n_roots, u32 *work_counter, const double *wsum, u64 *counters, int64_t first_slot = 0,
-                       int lane = 0, cudaStream_t st = nullptr)
+                       int lane = 0, cudaStream_t st = nullptr, int64_t first_group_of_day = 0)
 {
     if (!st) st = g->ctx->stream;
+    const Options &o = g->ctx->opt;
+    const size_t sw = slot_words(g, L.lay);
+    const size_t ws_lane = (size_t)lane * g->ws_ctas * 4 * (size_t)g->near_gcap;
+    if (L.gfn) {
+        GroupParams p;
+        p.ellw = rows;
+        p.row_ptr = g->row_ptr.p;
+        p.arcs = arcs;
+        p.pool = g->pool.p + (size_t)first_slot * sw;
+        p.slot_stride = sw;
+        p.roots = d_roots;
+        p.n_roots = n_roots;
+        p.n_groups = (n_roots + L.lay.K - 1) / L.lay.K;
+        p.V = (u32)g->V;
+        p.work_counter = work_counter;
+        p.wsum = wsum;
+        p.delta_scale = g->S > 0 ? o.delta_factor / (double)g->S : 0.0;
+        p.lag_factor = o.lag_factor;
+        p.ws_v = g->ws_v.p + ws_lane;
+        p.ws_k = reinterpret_cast<u32 *>(g->ws_d.p) + ws_lane;
+        p.near_scap = L.scap;
+        p.near_gcap = g->near_gcap;
+        p.far_cap = g->far_cap;
+        p.adaptive = (u32)o.adaptive_delta;
+        p.early_advance = (u32)(o.early_advance * (L.block / o.group_lanes) / 8);
+        p.counters = counters;
+        p.group_log = o.group_log && g->glog.p ? g->glog.p + (size_t)first_group_of_day * 4 : nullptr;
+        const int grid = std::min(L.grid, std::max(1, p.n_groups));
+        L.gfn<<<grid, L.block, L.smem, st>>>(p);
+        CU(cudaGetLastError());
+        return S4_OK;
+    }
     SsspParams p;
-    p.ell = ell;
+    p.ell = rows;
     p.row_ptr = g->row_ptr.p;
     p.arcs = arcs;
-    p.slot_stride = (size_t)((g->V + 3) & ~3);
+    p.slot_stride = sw;
     p.dist_pool = g->pool.p + (size_t)first_slot * p.slot_stride;
     p.roots = d_roots;
     p.n_roots = n_roots;
     p.V = (u32)g->V;
     p.work_counter = work_counter;
     p.wsum = wsum;
-    p.delta_scale = g->S > 0 ? g->ctx->opt.delta_factor / (double)g->S : 0.0;
-    p.ws_v = g->ws_v.p + (size_t)lane * g->ws_ctas * 4 * (size_t)g->near_gcap;
-    p.ws_d = g->ws_d.p + (size_t)lane * g->ws_ctas * 4 * (size_t)g->near_gcap;
+    p.delta_scale = g->S > 0 ? o.delta_factor / (double)g->S : 0.0;
+    p.ws_v = g->ws_v.p + ws_lane;
+    p.ws_d = g->ws_d.p + ws_lane;
     p.near_scap = L.scap;
     p.near_gcap = g->near_gcap;
     p.far_cap = g->far_cap;
-    p.preread = (u32)g->ctx->opt.preread;
-    p.adaptive = (u32)g->ctx->opt.adaptive_delta;
-    p.early_advance = (u32)(g->ctx->opt.early_advance * L.block / 8);
+    p.preread = (u32)o.preread;
+    p.adaptive = (u32)o.adaptive_delta;
+    p.early_advance = (u32)(o.early_advance * L.block / 8);
     p.counters = counters;
     const int grid = std::min(L.grid, std::max(1, n_roots));
     L.fn<<<grid, L.block, L.smem, st>>>(p);
@@ -660,17 +832,17 @@ static int launch_sssp(s4_graph *g, const SsspLaunch &L, const Arc *ell, const A
     return S4_OK;
 }
 
-static int launch_pred(s4_graph *g, const Arc *arcs, const u64 *dist, u32 root, int32_t *pred, double *dist_out)
+static int launch_pred(s4_graph *g, const Arc *arcs, const u64 *dist, u32 stride, u32 root, int32_t *pred, double *dist_out)
 {
     const int tile = g->ctx->opt.walk_tile ? g->ctx->opt.walk_tile : g->auto_walk_tile;
     const int block = 256;
     const int grid = grid_for((int64_t)g->V * tile, block, g->ctx);
     cudaStream_t st = g->ctx->stream;
     switch (tile) {
-        case 4: pred_kernel<4><<<grid, block, 0, st>>>(g->row_ptr.p, arcs, g->orig.p, dist, (u32)g->V, root, pred, dist_out); break;
-        case 8: pred_kernel<8><<<grid, block, 0, st>>>(g->row_ptr.p, arcs, g->orig.p, dist, (u32)g->V, root, pred, dist_out); break;
-        case 16: pred_kernel<16><<<grid, block, 0, st>>>(g->row_ptr.p, arcs, g->orig.p, dist, (u32)g->V, root, pred, dist_out); break;
-        default: pred_kernel<32><<<grid, block, 0, st>>>(g->row_ptr.p, arcs, g->orig.p, dist, (u32)g->V, root, pred, dist_out); break;
+        case 4: pred_kernel<4><<<grid, block, 0, st>>>(g->row_ptr.p, arcs, g->orig.p, dist, stride, (u32)g->V, root, pred, dist_out); break;
+        case 8: pred_kernel<8><<<grid, block, 0, st>>>(g->row_ptr.p, arcs, g->orig.p, dist, stride, (u32)g->V, root, pred, dist_out); break;
+        case 16: pred_kernel<16><<<grid, block, 0, st>>>(g->row_ptr.p, arcs, g->orig.p, dist, stride, (u32)g->V, root, pred, dist_out); break;
+        default: pred_kernel<32><<<grid, block, 0, st>>>(g->row_ptr.p, arcs, g->orig.p, dist, stride, (u32)g->V, root, pred, dist_out); break;
     }
     CU(cudaGetLastError());
     return S4_OK;
@@ -726,13 +898,17 @@ extern "C" int s4_graph_sssp(s4_graph *g, const double *w_street, int32_t origin
         weights_arc_kernel<<<grid_for(g->A, 256, ctx), 256, 0, st>>>(g->A, g->arc_cs.p, g->w_tmp.p, g->arcs_tmp.p);
         CU(cudaGetLastError());
     }
-    weights_ell_kernel<<<grid_for((int64_t)g->V * kEllWidth, 256, ctx), 256, 0, st>>>((int64_t)g->V * kEllWidth, g->ell_cs.p,
-                                                                                     g->w_tmp.p, g->ell_tmp.p);
+    if (L.gfn)
+        weights_ellw_kernel<<<grid_for((int64_t)g->V * kEllWidth, 256, ctx), 256, 0, st>>>((int64_t)g->V * kEllWidth, g->ell_cs.p,
+                                                                                          g->w_tmp.p, g->ell_tmp.p);
+    else
+        weights_ell_kernel<<<grid_for((int64_t)g->V * kEllWidth, 256, ctx), 256, 0, st>>>((int64_t)g->V * kEllWidth, g->ell_cs.p,
+                                                                                         g->w_tmp.p, g->ell_tmp.p);
     CU(cudaGetLastError());
     rc = launch_sssp(g, L, g->ell_tmp.p, g->arcs_tmp.p, g->root_tmp.p, 1, g->work_counters.p, g->wsum_tmp.p, g->ctr_tmp.p);
     if (rc) return rc;
-    // predecessors and distances come back in the caller's numbering
-    rc = launch_pred(g, g->arcs_tmp.p, g->pool.p, (u32)origin_dev, g->pred_tmp.p, g->dist_tmp.p);
+    // predecessors and distances come back in the caller's numbering (the tree is word 0 of the slot's rows)
+    rc = launch_pred(g, g->arcs_tmp.p, g->pool.p, (u32)L.lay.RW, (u32)origin_dev, g->pred_tmp.p, g->dist_tmp.p);
     if (rc) return rc;
     if (pred_out) CU(cudaMemcpyAsync(pred_out, g->pred_tmp.p, (size_t)g->V * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     if (dist_out) CU(cudaMemcpyAsync(dist_out, g->dist_tmp.p, (size_t)g->V * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -780,8 +956,6 @@ static int sim_alloc(s4_graph *g, s4_sim *sim, int64_t T, double jam_tolerance, 
     CU(sim->ms_ins.alloc((size_t)std::max<int64_t>(S, 1)));
     CU(sim->w_street.alloc((size_t)std::max<int64_t>(S, 1)));
     CU(sim->arcs.alloc((size_t)std::max<int64_t>(A, 1)));
-    CU(sim->ell.alloc((size_t)g->V * kEllWidth));
-    if (ctx->opt.walk_ell) CU(sim->ellw.alloc((size_t)g->V * kEllWidth));
     CU(sim->wsum.alloc(1));
     CU(sim->counters.alloc(C_COUNT));
     CU(cudaMemsetAsync(sim->load.p, 0, (size_t)std::max<int64_t>(S, 1) * sizeof(u32), st));   // simulation.py:43
@@ -812,9 +986,13 @@ static int sim_group(s4_sim *sim, DevBuf<u32> &kin, DevBuf<u32> &vin)
     DevBuf<unsigned char> tmp;
     CU(kout.alloc((size_t)T)); CU(vout.alloc((size_t)T));
     CU(flag.alloc((size_t)T)); CU(rank.alloc((size_t)T));
+    const int grid = grid_for(T, 256, ctx);
+    // trips are sorted by the position of their root in the grouping order (graph upload): the roots of a day then
+    // come out in that order, and consecutive roots are close in the graph
+    gather_u32_kernel<<<grid, 256, 0, st>>>(T, kin.p, g->gorder.p);
+    CU(cudaGetLastError());
     int rc = cub_sort_pairs(ctx, tmp, kin.p, kout.p, vin.p, vout.p, T);
     if (rc) return rc;
-    const int grid = grid_for(T, 256, ctx);
     head_flag_kernel<<<grid, 256, 0, st>>>(T, (const int32_t *)kout.p, flag.p);
     CU(cudaGetLastError());
     size_t bytes = 0;
@@ -829,7 +1007,7 @@ static int sim_group(s4_sim *sim, DevBuf<u32> &kin, DevBuf<u32> &vin)
     CU(off.alloc((size_t)D + 1));
     CU(sim->trip_root.alloc((size_t)T));
     CU(sim->trip_target.alloc((size_t)T));
-    group_scatter_kernel<<<grid, 256, 0, st>>>(T, (const int32_t *)kout.p, flag.p, rank.p, sim->trip_root.p, sim->roots.p, off.p);
+    group_scatter_kernel<<<grid, 256, 0, st>>>(T, (const int32_t *)kout.p, flag.p, rank.p, g->ginv.p, sim->trip_root.p, sim->roots.p, off.p);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(sim->trip_target.p, vout.p, (size_t)T * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
     sim->h_root_off.resize((size_t)D + 1);
@@ -1068,16 +1246,22 @@ static int run_weights(s4_sim *sim, int reset_load)
         CU(cudaGetLastError());
         ++sim->acc.kernel_launches;
     }
-    weights_ell_kernel<<<grid_for((int64_t)g->V * kEllWidth, 256, ctx), 256, 0, st>>>((int64_t)g->V * kEllWidth, g->ell_cs.p,
-                                                                                     sim->w_street.p, sim->ell.p);
-    CU(cudaGetLastError());
-    if (sim->ellw.p) {
-        weights_ellw_kernel<<<grid_for((int64_t)g->V * kEllWidth, 256, ctx), 256, 0, st>>>((int64_t)g->V * kEllWidth, g->ell_cs.p,
-                                                                                          sim->w_street.p, sim->ellw.p);
+    // fixed-stride rows: the source-batched SSSP and the walk share one table {head, street_index, w}; the
+    // one-tree-per-CTA kernel reads its own ({head, entry word, w})
+    const bool grouped = ctx->opt.group_lanes > 0;
+    const int64_t n_slots = (int64_t)g->V * kEllWidth;
+    if (!grouped) {
+        CU(sim->ell.ensure((size_t)n_slots));
+        weights_ell_kernel<<<grid_for(n_slots, 256, ctx), 256, 0, st>>>(n_slots, g->ell_cs.p, sim->w_street.p, sim->ell.p);
         CU(cudaGetLastError());
         ++sim->acc.kernel_launches;
     }
-    ++sim->acc.kernel_launches;
+    if (grouped || ctx->opt.walk_ell) {
+        CU(sim->ellw.ensure((size_t)n_slots));
+        weights_ellw_kernel<<<grid_for(n_slots, 256, ctx), 256, 0, st>>>(n_slots, g->ell_cs.p, sim->w_street.p, sim->ellw.p);
+        CU(cudaGetLastError());
+        ++sim->acc.kernel_launches;
+    }
     sim->weights_valid = true;
     return S4_OK;
 }
@@ -1109,7 +1293,10 @@ extern "C" int s4_sim_step(s4_sim *sim)
     if (rc) return rc;
     SsspLaunch L;
     if ((rc = plan_sssp(g, &L))) return rc;
-    if (sim->D > 0 && (rc = ensure_scratch(g, L, sim->D))) return rc;
+    const int64_t K = L.lay.K;
+    const int64_t D = sim->D;
+    const int64_t G = (D + K - 1) / K;                             // slots (groups of K trees) the day needs
+    if (D > 0 && (rc = ensure_scratch(g, L, G))) return rc;
 
     if ((rc = ev_begin(sim->ev_step, sim->used_step, st))) return rc;
     // ---- K1 (simulation.py:53-65) + reset of today's counters (:68)
@@ -1117,17 +1304,22 @@ extern "C" int s4_sim_step(s4_sim *sim)
     if ((rc = run_weights(sim, 1))) return rc;
     if ((rc = ev_end(sim->ev_w, sim->used_w, st))) return rc;
 
-    // ---- K2 + K3 in batches (simulation.py:71-88).  With more than one batch the work runs in two
-    // independent lanes (own stream, own half of the distance pool, own frontier workspace): batch i goes
-    // to lane i & 1, where its SSSP launch is followed by its walk.  The persistent SSSP grid of one lane
-    // fills the SMs the other lane's launch frees while it drains its last trees, and the walk (a
-    // latency-bound pointer chase) hides under the other lane's SSSP.
-    const int64_t D = sim->D;
+    // ---- K2 + K3 in batches (simulation.py:71-88).  The work runs in two independent lanes (own stream, own
+    // half of the distance pool, own frontier workspace): batch i goes to lane i & 1, where its SSSP launch is
+    // followed by its walk.  The persistent SSSP grid of one lane fills the SMs the other lane's launch frees
+    // while it drains its last trees, and the walk (a latency-bound pointer chase) hides under the other lane's
+    // SSSP.  A day is cut into at least `min_batches` batches even when all its trees would fit the pool at once.
     const int64_t slots = std::max<int64_t>(1, g->pool_slots);
-    const bool halves = D > slots && slots >= 2;                   // launch size: half the pool
-    const bool split = halves && ctx->opt.lanes >= 2;              // ... and the halves run as concurrent lanes
-    const int64_t B = halves ? slots / 2 : slots;
-    const int64_t n_batches = (D + B - 1) / B;
+    const bool split = ctx->opt.lanes >= 2 && slots >= 2 && G >= 2;
+    int64_t B = split ? slots / 2 : slots;                         // slots per launch
+    if (split) B = std::min(B, std::max<int64_t>(1, (G + ctx->opt.min_batches - 1) / ctx->opt.min_batches));
+    const int64_t n_batches = G > 0 ? (G + B - 1) / B : 0;
+    g->glog_groups = 0;
+    if (ctx->opt.group_log && L.gfn && G > 0) {
+        CU(g->glog.ensure((size_t)G * 4));
+        CU(cudaMemsetAsync(g->glog.p, 0, (size_t)G * 4 * sizeof(u32), st));
+        g->glog_groups = G;
+    }
     if (n_batches > 0) {
         CU(g->work_counters.ensure((size_t)std::max<int64_t>(n_batches, 1024)));
         CU(cudaMemsetAsync(g->work_counters.p, 0, g->work_counters.n * sizeof(u32), st));
@@ -1136,14 +1328,15 @@ extern "C" int s4_sim_step(s4_sim *sim)
         CU(cudaEventRecord(ctx->sssp_done[0], st));
         CU(cudaStreamWaitEvent(ctx->walk_stream, ctx->sssp_done[0], 0));
     }
+    const size_t sw = slot_words(g, L.lay);
     for (int64_t bi = 0; bi < n_batches; ++bi) {
-        const int64_t r0 = bi * B, r1 = std::min(D, r0 + B);
+        const int64_t r0 = bi * B * K, r1 = std::min(D, r0 + B * K);
         const int lane = split ? (int)(bi & 1) : 0;
         cudaStream_t ls = lane ? ctx->walk_stream : st;
-        const int64_t first_slot = lane * B;
+        const int64_t first_slot = lane * (slots / 2);
         if ((rc = ev_begin(sim->ev_sssp, sim->used_sssp, ls))) return rc;
-        if ((rc = launch_sssp(g, L, sim->ell.p, sim->arcs.p, sim->roots.p + r0, (int)(r1 - r0), g->work_counters.p + bi,
-                              sim->wsum.p, sim->counters.p, first_slot, lane, ls))) return rc;
+        if ((rc = launch_sssp(g, L, L.gfn ? sim->ellw.p : sim->ell.p, sim->arcs.p, sim->roots.p + r0, (int)(r1 - r0),
+                              g->work_counters.p + bi, sim->wsum.p, sim->counters.p, first_slot, lane, ls, bi * B))) return rc;
         if ((rc = ev_end(sim->ev_sssp, sim->used_sssp, ls))) return rc;
         ++sim->acc.kernel_launches;
         ++sim->acc.sssp_launches;
@@ -1152,8 +1345,10 @@ extern "C" int s4_sim_step(s4_sim *sim)
         wp.arcs = sim->arcs.p;
         wp.ellw = ctx->opt.walk_ell ? sim->ellw.p : nullptr;
         wp.orig = g->orig.p;
-        wp.slot_stride = (size_t)((g->V + 3) & ~3);
-        wp.dist_pool = g->pool.p + (size_t)first_slot * wp.slot_stride;
+        wp.slot_stride = sw;
+        wp.group = (u32)K;
+        wp.node_stride = (u32)L.lay.RW;
+        wp.dist_pool = g->pool.p + (size_t)first_slot * sw;
         wp.roots = sim->roots.p;
         wp.trip_target = sim->trip_target.p;
         wp.trip_root = sim->trip_root.p;

@@ -617,7 +617,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024
 template <int TILE, bool WANT_ID>
 __device__ __forceinline__ u64 canonical_pred(const cg::thread_block_tile<TILE> &tile, const u32 *__restrict__ row_ptr,
                                               const Arc *__restrict__ arcs, const u32 *__restrict__ orig, const u64 *dist,
-                                              u32 cur, u64 dv, u32 *col_out, u64 *du_out)
+                                              u32 stride, u32 cur, u64 dv, u32 *col_out, u64 *du_out)
 {
     const u32 rb = __ldg(row_ptr + cur), re = __ldg(row_ptr + cur + 1);
     // pass 1: which arcs reproduce dist[cur] exactly?  Almost always exactly one (unique shortest path):
@@ -628,7 +628,7 @@ __device__ __forceinline__ u64 canonical_pred(const cg::thread_block_tile<TILE> 
         if (e < re) {
             const Arc a = ld_arc(arcs + e);
             if (a.col != cur) {
-                const u64 du = ld_dist(dist + a.col);
+                const u64 du = ld_dist(dist + (size_t)a.col * stride);
                 const u64 ndb = (u64)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)du), a.w));
                 if (du < kInfBits && ndb == dv) { ++n_cand; key1 = a.street; du1 = du; col1 = a.col; }
             }
@@ -654,7 +654,7 @@ __device__ __forceinline__ u64 canonical_pred(const cg::thread_block_tile<TILE> 
         if (e < re) {
             const Arc a = ld_arc(arcs + e);
             if (a.col != cur) {
-                const u64 du = ld_dist(dist + a.col);
+                const u64 du = ld_dist(dist + (size_t)a.col * stride);
                 const u64 ndb = (u64)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)du), a.w));
                 if (du < kInfBits && ndb == dv) {
                     const u32 id_u = orig ? __ldg(orig + a.col) : a.col;
@@ -686,7 +686,7 @@ __device__ __forceinline__ u64 canonical_pred(const cg::thread_block_tile<TILE> 
 template <int TILE, bool WANT_ID>
 __device__ __forceinline__ u64 canonical_pred_ell(const cg::thread_block_tile<TILE> &tile, const Arc *__restrict__ ellw,
                                                   const u32 *__restrict__ row_ptr, const Arc *__restrict__ arcs,
-                                                  const u32 *__restrict__ orig, const u64 *dist, u32 cur, u64 dv,
+                                                  const u32 *__restrict__ orig, const u64 *dist, u32 stride, u32 cur, u64 dv,
                                                   u32 *col_out, u64 *du_out)
 {
     static_assert(TILE >= kEllWidth, "one lane per slot");
@@ -695,12 +695,12 @@ __device__ __forceinline__ u64 canonical_pred_ell(const cg::thread_block_tile<TI
     a.col = cur; a.street = 0u; a.w = 0.0;
     if (lane < (u32)kEllWidth) a = ld_arc(ellw + (size_t)cur * kEllWidth + lane);
     if (tile.any(lane == 0u && (a.col & kOvfBit) != 0u))
-        return canonical_pred<TILE, WANT_ID>(tile, row_ptr, arcs, orig, dist, cur, dv, col_out, du_out);
+        return canonical_pred<TILE, WANT_ID>(tile, row_ptr, arcs, orig, dist, stride, cur, dv, col_out, du_out);
     const u32 col = a.col;
     u64 du = 0;
     bool match = false;
     if (lane < (u32)kEllWidth && col != cur) {
-        du = ld_dist(dist + col);
+        du = ld_dist(dist + (size_t)col * stride);
         const u64 ndb = (u64)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)du), a.w));
         match = du < kInfBits && ndb == dv;
     }
@@ -750,8 +750,10 @@ struct WalkParams {
     const Arc *arcs;
     const Arc *ellw;            // fixed-stride rows with street indices (nullptr: CSR only)
     const u32 *orig;            // device number -> caller's node id (nullptr = identity)
-    const u64 *dist_pool;
-    size_t slot_stride;
+    const u64 *dist_pool;       // first slot of this batch
+    size_t slot_stride;         // words per slot (a slot holds the rows of `group` trees)
+    u32 group;                  // trees per slot: tree i of the batch is word i % group of the rows of slot i / group
+    u32 node_stride;            // words per row (1 = one tree per slot, plain dist[V])
     const int32_t *roots;       // distinct roots (all of them), device numbers
     const int32_t *trip_target; // trips sorted by root, device numbers
     const u32 *trip_root;       // index of the trip's root among the distinct roots
@@ -774,17 +776,19 @@ __global__ void __launch_bounds__(256) walk_kernel(WalkParams p)
     for (int64_t t = p.t0 + tile_id; t < p.t1; t += tiles_per_grid) {
         const u32 ri = p.trip_root[t];
         const u32 root = (u32)p.roots[ri];
-        const u64 *dist = p.dist_pool + (size_t)(ri - p.root0) * p.slot_stride;
+        const u32 ti = ri - p.root0;
+        const u64 *dist = p.dist_pool + (size_t)(ti / p.group) * p.slot_stride + (ti % p.group);
+        const u32 stride = p.node_stride;
         u32 cur = (u32)p.trip_target[t];
-        u64 dv = ld_dist(dist + cur);
+        u64 dv = ld_dist(dist + (size_t)cur * stride);
         ++c_trips;
         if (dv >= kInfBits) { ++c_unreach; continue; }                     // simulation.py:80
         u32 guard = 0;
         while (cur != root) {                                              // :83
             u64 du;
             u32 nxt;
-            const u64 key = p.ellw ? canonical_pred_ell<TILE, false>(tile, p.ellw, p.row_ptr, p.arcs, p.orig, dist, cur, dv, &nxt, &du)
-                                   : canonical_pred<TILE, false>(tile, p.row_ptr, p.arcs, p.orig, dist, cur, dv, &nxt, &du);
+            const u64 key = p.ellw ? canonical_pred_ell<TILE, false>(tile, p.ellw, p.row_ptr, p.arcs, p.orig, dist, stride, cur, dv, &nxt, &du)
+                                   : canonical_pred<TILE, false>(tile, p.row_ptr, p.arcs, p.orig, dist, stride, cur, dv, &nxt, &du);
             if (key == ~0ull || ++guard > p.V) { ++c_stuck; break; }
             if (tile.thread_rank() == 0) atomicAdd(p.load + (u32)key, p.volume);   // :86-88
             ++c_hops;
@@ -804,18 +808,18 @@ __global__ void __launch_bounds__(256) walk_kernel(WalkParams p)
 // (StreetNetwork.calculate_shortest_paths, streetnetwork.py:108-109)
 template <int TILE>
 __global__ void __launch_bounds__(256) pred_kernel(const u32 *row_ptr, const Arc *arcs, const u32 *orig, const u64 *dist,
-                                                   u32 V, u32 root, int32_t *pred_out, double *dist_out)
+                                                   u32 stride, u32 V, u32 root, int32_t *pred_out, double *dist_out)
 {
     cg::thread_block block = cg::this_thread_block();
     cg::thread_block_tile<TILE> tile = cg::tiled_partition<TILE>(block);
     const u32 tiles_per_grid = gridDim.x * (blockDim.x / TILE);
     for (u32 v = blockIdx.x * (blockDim.x / TILE) + threadIdx.x / TILE; v < V; v += tiles_per_grid) {
-        const u64 dv = ld_dist(dist + v);
+        const u64 dv = ld_dist(dist + (size_t)v * stride);
         int32_t pr = -1;
         if (v != root && dv < kInfBits) {
             u64 du;
             u32 nxt;
-            const u64 key = canonical_pred<TILE, true>(tile, row_ptr, arcs, orig, dist, v, dv, &nxt, &du);
+            const u64 key = canonical_pred<TILE, true>(tile, row_ptr, arcs, orig, dist, stride, v, dv, &nxt, &du);
             if (key != ~0ull) pr = (int32_t)(key >> 32);
         }
         if (tile.thread_rank() == 0) {
@@ -882,15 +886,23 @@ __global__ void head_flag_kernel(int64_t T, const int32_t *__restrict__ sorted_r
 }
 
 // rank[i] = inclusive_scan(flag)[i]; root index = rank-1; heads record root node and first-trip offset
+// (sorted_root holds positions in the grouping order; ginv maps a position back to the node)
 __global__ void group_scatter_kernel(int64_t T, const int32_t *__restrict__ sorted_root, const u32 *__restrict__ flag,
-                                     const u32 *__restrict__ rank, u32 *__restrict__ trip_root,
+                                     const u32 *__restrict__ rank, const u32 *__restrict__ ginv, u32 *__restrict__ trip_root,
                                      int32_t *__restrict__ roots, int64_t *__restrict__ root_off)
 {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < T; i += (int64_t)gridDim.x * blockDim.x) {
         const u32 r = rank[i] - 1u;
         trip_root[i] = r;
-        if (flag[i]) { roots[r] = sorted_root[i]; root_off[r] = i; }
+        if (flag[i]) { roots[r] = (int32_t)ginv[sorted_root[i]]; root_off[r] = i; }
     }
+}
+
+// x[i] = table[x[i]]
+__global__ void gather_u32_kernel(int64_t n, u32 *__restrict__ x, const u32 *__restrict__ table)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        x[i] = table[x[i]];
 }
 
 // ---------------------------------------------------------------------------

@@ -127,6 +127,16 @@ class DeviceGraph(object):
         except Exception:
             pass
 
+    def group_log(self):
+        """Diagnostics of the last day (option group_log=1): uint32[n_groups, 4] = SM cycles >> 10, rounds,
+        entries popped, bucket advances per group of trees."""
+        n = C.c_int64()
+        check(self.lib.s4_graph_group_log(self._h, None, 0, C.byref(n)))
+        out = np.zeros(max(n.value, 0), dtype=np.uint32)
+        if n.value:
+            check(self.lib.s4_graph_group_log(self._h, ptr(out, C.c_uint32), n.value, C.byref(n)))
+        return out.reshape(-1, 4)
+
     def sssp(self, w_street, origin, want_pred=True):
         """(dist float64[V], pred int32[V]) of one tree."""
         w = as_array(w_street, np.float64)

@@ -87,10 +87,13 @@ class FlatNetwork(object):
     def S(self):
         return len(self.u)
 
-    def locality_rank(self):
-        """Position of every node along a Z-order (Morton) curve over the rank-quantised coordinates,
-        or None when the coordinates carry no information.  Pure memory-layout hint for the device
-        (neighbouring nodes share cache sectors); no result depends on it."""
+    def locality_rank(self, curve="hilbert"):
+        """Position of every node along a space-filling curve over the rank-quantised coordinates (Hilbert by
+        default, "morton" for the Z-order curve), or None when the coordinates carry no information.  Pure
+        memory-layout hint for the device: neighbouring nodes get neighbouring numbers, and the roots of a day,
+        sorted by that number, fall into spatially compact groups (the source-batched SSSP kernel runs one group
+        of trees per CTA; the Hilbert curve has no jumps, so no group straddles a quadrant boundary).  No result
+        depends on it."""
         if self.lon is None or self.lat is None or len(self.node_ids) < 8:
             return None
         if np.ptp(self.lon) == 0 and np.ptp(self.lat) == 0:
@@ -102,14 +105,30 @@ class FlatNetwork(object):
             r[np.argsort(x, kind="stable")] = np.arange(n, dtype=np.uint64)
             return (r * np.uint64(65536)) // np.uint64(n)
 
-        def spread(x):
-            x = (x | (x << np.uint64(8))) & np.uint64(0x00FF00FF)
-            x = (x | (x << np.uint64(4))) & np.uint64(0x0F0F0F0F)
-            x = (x | (x << np.uint64(2))) & np.uint64(0x33333333)
-            x = (x | (x << np.uint64(1))) & np.uint64(0x55555555)
-            return x
-
-        key = spread(quantise(self.lon)) | (spread(quantise(self.lat)) << np.uint64(1))
+        qx, qy = quantise(self.lon), quantise(self.lat)
+        if curve == "morton":
+            def spread(x):
+                x = (x | (x << np.uint64(8))) & np.uint64(0x00FF00FF)
+                x = (x | (x << np.uint64(4))) & np.uint64(0x0F0F0F0F)
+                x = (x | (x << np.uint64(2))) & np.uint64(0x33333333)
+                x = (x | (x << np.uint64(1))) & np.uint64(0x55555555)
+                return x
+            key = spread(qx) | (spread(qy) << np.uint64(1))
+        else:
+            # Hilbert index of (qx, qy) on the 65536 x 65536 lattice, one bit plane per step (vectorised xy2d)
+            x, y = qx.astype(np.int64), qy.astype(np.int64)
+            key = np.zeros(n, dtype=np.int64)
+            s = 32768
+            while s > 0:
+                rx = ((x & s) > 0).astype(np.int64)
+                ry = ((y & s) > 0).astype(np.int64)
+                key += s * s * ((3 * rx) ^ ry)
+                flip = (ry == 0) & (rx == 1)
+                x = np.where(flip, s - 1 - x, x)
+                y = np.where(flip, s - 1 - y, y)
+                swap = ry == 0
+                x, y = np.where(swap, y, x), np.where(swap, x, y)
+                s //= 2
         rank = np.empty(n, dtype=np.int32)
         rank[np.argsort(key, kind="stable")] = np.arange(n, dtype=np.int32)
         return rank

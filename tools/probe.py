@@ -19,6 +19,7 @@ ap.add_argument("--configs", type=str, default="")
 ap.add_argument("--days", type=int, default=2)
 ap.add_argument("--morton", type=int, default=0)
 ap.add_argument("--rank", type=int, default=1)
+ap.add_argument("--goals", type=int, default=0, help="1: the trees are rooted at the cfg3 goal sample (2 %% of the nodes), like a bench day")
 args = ap.parse_args()
 
 dev = engine.default_device()
@@ -44,6 +45,10 @@ cats = synth.node_categories(arr["node_ids"], seed=1)
 rng = np.random.default_rng(0)
 origins = rng.choice(arr["node_ids"], size=args.roots, replace=False)
 goals = cats["goals"][rng.integers(0, len(cats["goals"]), size=args.roots)]
+if args.goals:
+    goals = cats["goals"] if args.roots <= 0 else cats["goals"][: args.roots]
+    origins = rng.choice(arr["node_ids"], size=len(goals))
+    dev.set_option("root_mode", 1)
 phys = engine.make_physics(settings)
 rank = synth.network_from(arr).flat().locality_rank() if args.rank else None
 g = engine.DeviceGraph(dev, V, arr["u"], arr["v"], arr["length"], arr["max_speed"], node_rank=rank)
@@ -77,6 +82,15 @@ for cfg in configs:
                push_x=round(c["queue_pushes"] / max(1, c["nodes_algorithmic"]), 2),
                rounds=c["relax_rounds"] // sim.n_roots, adv=c["bucket_advances"] // sim.n_roots,
                fb=c["fallback_sweeps"], hops=c["hops"])
+    if cfg.get("group_log"):
+        gl = g.group_log().astype(np.float64)
+        if len(gl):
+            cyc = gl[:, 0] * 1024 / 1.965e6      # ms at 1965 MHz
+            q = lambda a: [round(float(x), 1) for x in np.percentile(a, [0, 10, 50, 90, 99, 100])]
+            out["group_ms_pct"] = q(cyc)
+            out["group_rounds_pct"] = q(gl[:, 1])
+            out["group_exp_per_node_pct"] = [round(x / V, 2) for x in np.percentile(gl[:, 2], [0, 10, 50, 90, 99, 100])]
+            out["group_ms_sum_over_sms"] = round(float(cyc.sum()) / dev.info()["sm_count"], 1)
     print(json.dumps(out), flush=True)
     sim.close()
     for k, v in base.items():
