@@ -137,6 +137,7 @@ struct s4_graph {
     DevBuf<u32> orig;          // device number -> caller's dense id (empty = identity numbering)
     std::vector<int32_t> rank; // caller's dense id -> device number (empty = identity)
     std::vector<int32_t> max_speed0;   // host copy of the uploaded limits
+    std::vector<u32> row_ptr_h, col_h;  // host copy of the CSR (device numbering): root clustering at simulation setup
     std::vector<u32> gorder_h, ginv_h;  // grouping order of tree roots: device number -> position / position -> device number
     DevBuf<u32> gorder, ginv;
     // connected components (host): algorithmic arcs / nodes of a tree rooted at r
@@ -172,10 +173,21 @@ struct s4_sim {
     double jam = 0.0;
     Phys ph{};
     u32 volume = 1;
-    DevBuf<int32_t> trip_target;   // T, sorted by root
-    DevBuf<u32> trip_root;         // T
-    DevBuf<int32_t> roots;         // D
-    std::vector<int64_t> h_root_off;   // D+1
+    // trips sorted by root, roots in the grouping order of the graph (canonical form, independent of the kernel) ...
+    DevBuf<int32_t> trip_target0;  // T
+    DevBuf<u32> trip_root0;        // T, index into roots0
+    DevBuf<int32_t> roots0;        // D
+    DevBuf<int64_t> root_off0;     // D (+1), first trip of every root
+    std::vector<int32_t> h_roots0;     // D
+    std::vector<int64_t> h_root_off0;  // D+1
+    // ... and as the kernels consume them: roots clustered into groups of `grouped_K` trees (slots padded with -1),
+    // trips in the order of those slots
+    int grouped_K = 0;
+    int64_t Dp = 0;                // slots = groups * grouped_K
+    DevBuf<int32_t> trip_target;   // T
+    DevBuf<u32> trip_root;         // T, index into roots
+    DevBuf<int32_t> roots;         // Dp
+    std::vector<int64_t> h_root_off;   // Dp+1
     int64_t alg_arcs_per_day = 0, alg_nodes_per_day = 0;
     DevBuf<u32> load, cum;
     bool has_cum = false;
@@ -429,6 +441,9 @@ extern "C" int s4_graph_upload(s4_ctx *ctx, int32_t V, int64_t S, const int32_t 
     }
     s4_graph *g = new (std::nothrow) s4_graph();
     if (!g) return fail(S4_ERR_OOM, "host allocation failed");
+    g->row_ptr_h = row_ptr;
+    g->col_h.resize((size_t)A);
+    for (int64_t e = 0; e < A; ++e) g->col_h[(size_t)e] = arc_cs[(size_t)e].x;
     g->ctx = ctx;
     ++ctx->refs;
     g->V = V;
@@ -977,12 +992,12 @@ static int sim_group(s4_sim *sim, DevBuf<u32> &kin, DevBuf<u32> &vin)
     cudaStream_t st = ctx->stream;
     const int64_t T = sim->T;
     if (T == 0) {
+        sim->h_root_off0.assign(1, 0);
         sim->h_root_off.assign(1, 0);
         CU(cudaStreamSynchronize(st));
         return S4_OK;
     }
     DevBuf<u32> kout, vout, flag, rank;
-    DevBuf<int64_t> off;
     DevBuf<unsigned char> tmp;
     CU(kout.alloc((size_t)T)); CU(vout.alloc((size_t)T));
     CU(flag.alloc((size_t)T)); CU(rank.alloc((size_t)T));
@@ -1003,24 +1018,114 @@ static int sim_group(s4_sim *sim, DevBuf<u32> &kin, DevBuf<u32> &vin)
     CU(cudaMemcpyAsync(&D, rank.p + (T - 1), sizeof(u32), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     sim->D = D;
-    CU(sim->roots.alloc((size_t)D));
-    CU(off.alloc((size_t)D + 1));
-    CU(sim->trip_root.alloc((size_t)T));
-    CU(sim->trip_target.alloc((size_t)T));
-    group_scatter_kernel<<<grid, 256, 0, st>>>(T, (const int32_t *)kout.p, flag.p, rank.p, g->ginv.p, sim->trip_root.p, sim->roots.p, off.p);
+    CU(sim->roots0.alloc((size_t)D));
+    CU(sim->root_off0.alloc((size_t)D + 1));
+    CU(sim->trip_root0.alloc((size_t)T));
+    CU(sim->trip_target0.alloc((size_t)T));
+    group_scatter_kernel<<<grid, 256, 0, st>>>(T, (const int32_t *)kout.p, flag.p, rank.p, g->ginv.p, sim->trip_root0.p, sim->roots0.p, sim->root_off0.p);
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(sim->trip_target.p, vout.p, (size_t)T * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
-    sim->h_root_off.resize((size_t)D + 1);
-    std::vector<int32_t> h_roots((size_t)D);
-    CU(cudaMemcpyAsync(sim->h_root_off.data(), off.p, (size_t)D * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(h_roots.data(), sim->roots.p, (size_t)D * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(sim->trip_target0.p, vout.p, (size_t)T * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    sim->h_root_off0.resize((size_t)D + 1);
+    sim->h_roots0.resize((size_t)D);
+    CU(cudaMemcpyAsync(sim->h_root_off0.data(), sim->root_off0.p, (size_t)D * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(sim->h_roots0.data(), sim->roots0.p, (size_t)D * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    sim->h_root_off[(size_t)D] = T;
+    sim->h_root_off0[(size_t)D] = T;
     for (u32 i = 0; i < D; ++i) {
-        const int32_t c = g->comp_of[(size_t)h_roots[i]];
+        const int32_t c = g->comp_of[(size_t)sim->h_roots0[i]];
         sim->alg_arcs_per_day += g->comp_arcs[(size_t)c];
         sim->alg_nodes_per_day += g->comp_nodes[(size_t)c];
     }
+    return S4_OK;
+}
+
+// Cluster the day's roots into groups of K trees that are close in the graph (the source-batched kernel runs a group
+// on one frontier: its trees should reach every node at about the same time).  Greedy: seeds in the grouping order of
+// the graph; a breadth-first search from an unassigned seed collects the unassigned roots it meets until it has K of
+// them or has visited 6 * K * V / D nodes (six times the ball that holds K roots on average); smaller groups are
+// padded with -1.  O(V) node visits in total.
+static void cluster_roots(const s4_graph *g, const std::vector<int32_t> &roots, int K, std::vector<int32_t> &slots,
+                          std::vector<int64_t> &slot_of)
+{
+    const int64_t D = (int64_t)roots.size(), V = g->V;
+    slots.clear();
+    slot_of.assign((size_t)D, -1);
+    if (K <= 1) {
+        slots.assign(roots.begin(), roots.end());
+        for (int64_t i = 0; i < D; ++i) slot_of[(size_t)i] = i;
+        return;
+    }
+    std::vector<int32_t> level((size_t)V, -1), queue, touched;
+    std::vector<int64_t> root_idx((size_t)V, -1);                   // node -> index among the roots while unassigned
+    for (int64_t i = 0; i < D; ++i) root_idx[(size_t)roots[(size_t)i]] = i;
+    const int64_t cap = std::max<int64_t>(64, 6 * (int64_t)K * V / std::max<int64_t>(1, D));
+    for (int64_t i = 0; i < D; ++i) {
+        const int32_t seed = roots[(size_t)i];
+        if (root_idx[(size_t)seed] < 0) continue;                   // already in a group
+        const size_t base = slots.size();
+        slots.resize(base + (size_t)K, -1);
+        queue.clear();
+        touched.clear();
+        queue.push_back(seed);
+        level[(size_t)seed] = 0;
+        touched.push_back(seed);
+        int got = 0;
+        for (size_t head = 0; head < queue.size() && got < K && (int64_t)head <= cap; ++head) {
+            const int32_t x = queue[head];
+            const int64_t ri = root_idx[(size_t)x];
+            if (ri >= 0) {
+                root_idx[(size_t)x] = -1;
+                slot_of[(size_t)ri] = (int64_t)(base + (size_t)got);
+                slots[base + (size_t)got++] = x;
+            }
+            for (u32 e = g->row_ptr_h[(size_t)x]; e < g->row_ptr_h[(size_t)x + 1]; ++e) {
+                const int32_t y = (int32_t)g->col_h[e];
+                if (level[(size_t)y] < 0) { level[(size_t)y] = level[(size_t)x] + 1; queue.push_back(y); touched.push_back(y); }
+            }
+        }
+        for (int32_t x : touched) level[(size_t)x] = -1;
+    }
+}
+
+// (re)build the arrays the kernels consume for groups of K trees
+static int sim_regroup(s4_sim *sim, int K)
+{
+    s4_graph *g = sim->g;
+    s4_ctx *ctx = g->ctx;
+    cudaStream_t st = ctx->stream;
+    const int64_t T = sim->T, D = sim->D;
+    sim->grouped_K = K;
+    if (T == 0 || D == 0) {
+        sim->Dp = 0;
+        sim->h_root_off.assign(1, 0);
+        return S4_OK;
+    }
+    std::vector<int32_t> slots;
+    std::vector<int64_t> slot_of;
+    cluster_roots(g, sim->h_roots0, K, slots, slot_of);
+    const int64_t Dp = (int64_t)slots.size();
+    sim->Dp = Dp;
+    // trips of slot j start at h_root_off[j]; empty for padding slots
+    std::vector<int64_t> count((size_t)Dp, 0), new_start((size_t)D);
+    for (int64_t i = 0; i < D; ++i) count[(size_t)slot_of[(size_t)i]] = sim->h_root_off0[(size_t)i + 1] - sim->h_root_off0[(size_t)i];
+    sim->h_root_off.assign((size_t)Dp + 1, 0);
+    for (int64_t j = 0; j < Dp; ++j) sim->h_root_off[(size_t)j + 1] = sim->h_root_off[(size_t)j] + count[(size_t)j];
+    std::vector<u32> slot_of32((size_t)D);
+    for (int64_t i = 0; i < D; ++i) { new_start[(size_t)i] = sim->h_root_off[(size_t)slot_of[(size_t)i]]; slot_of32[(size_t)i] = (u32)slot_of[(size_t)i]; }
+    DevBuf<int64_t> d_new_start;
+    DevBuf<u32> d_slot_of;
+    CU(d_new_start.alloc((size_t)D));
+    CU(d_slot_of.alloc((size_t)D));
+    CU(sim->roots.alloc((size_t)Dp));
+    CU(sim->trip_root.ensure((size_t)T));
+    CU(sim->trip_target.ensure((size_t)T));
+    CU(cudaMemcpyAsync(d_new_start.p, new_start.data(), (size_t)D * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_slot_of.p, slot_of32.data(), (size_t)D * sizeof(u32), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(sim->roots.p, slots.data(), (size_t)Dp * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    regroup_trips_kernel<<<grid_for(T, 256, ctx), 256, 0, st>>>(T, sim->trip_root0.p, sim->trip_target0.p, sim->root_off0.p, d_slot_of.p,
+                                                               d_new_start.p, sim->trip_root.p, sim->trip_target.p);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));                                  // the staging buffers go out of scope
     return S4_OK;
 }
 
@@ -1064,6 +1169,7 @@ extern "C" int s4_sim_create(s4_graph *g, int64_t T, const int32_t *origin, cons
         CU(cudaMemcpyAsync(vin.p, target_h, (size_t)T * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     }
     if ((rc = sim_group(sim, kin, vin))) return rc;
+    if ((rc = sim_regroup(sim, layout_of(ctx->opt).K))) return rc;
     guard.s = nullptr;
     ++g->refs;
     *out = sim;
@@ -1119,6 +1225,7 @@ extern "C" int s4_sim_create_sampled(s4_graph *g, int64_t T, int64_t n_origins, 
         CU(cudaStreamSynchronize(st));                                   // mr / mt / d_r / d_t go out of scope
     }
     if ((rc = sim_group(sim, kin, vin))) return rc;
+    if ((rc = sim_regroup(sim, layout_of(ctx->opt).K))) return rc;
     guard.s = nullptr;
     ++g->refs;
     *out = sim;
@@ -1132,7 +1239,7 @@ extern "C" int s4_sim_get_trips(s4_sim *sim, int32_t *origin_out, int32_t *goal_
     s4_graph *g = sim->g;
     s4_ctx *ctx = g->ctx;
     CU(cudaSetDevice(ctx->device));
-    const int64_t T = sim->T, D = sim->D;
+    const int64_t T = sim->T, D = sim->Dp;
     if (T == 0) return S4_OK;
     std::vector<u32> troot((size_t)T);
     std::vector<int32_t> ttarget((size_t)T), roots((size_t)D);
@@ -1294,8 +1401,9 @@ extern "C" int s4_sim_step(s4_sim *sim)
     SsspLaunch L;
     if ((rc = plan_sssp(g, &L))) return rc;
     const int64_t K = L.lay.K;
-    const int64_t D = sim->D;
-    const int64_t G = (D + K - 1) / K;                             // slots (groups of K trees) the day needs
+    if (sim->grouped_K != (int)K && (rc = sim_regroup(sim, (int)K))) return rc;   // the group size changed since the trips were set up
+    const int64_t D = sim->Dp;                                     // root slots (groups padded to K)
+    const int64_t G = D / K;                                       // slots of the distance pool the day needs
     if (D > 0 && (rc = ensure_scratch(g, L, G))) return rc;
 
     if ((rc = ev_begin(sim->ev_step, sim->used_step, st))) return rc;
@@ -1370,7 +1478,7 @@ extern "C" int s4_sim_step(s4_sim *sim)
     }
     if ((rc = ev_end(sim->ev_step, sim->used_step, st))) return rc;
     sim->acc.days += 1;
-    sim->acc.sssp_instances += (uint64_t)D;
+    sim->acc.sssp_instances += (uint64_t)sim->D;
     sim->acc.arcs_algorithmic += (uint64_t)sim->alg_arcs_per_day;
     sim->acc.nodes_algorithmic += (uint64_t)sim->alg_nodes_per_day;
     return S4_OK;

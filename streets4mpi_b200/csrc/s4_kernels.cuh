@@ -898,6 +898,19 @@ __global__ void group_scatter_kernel(int64_t T, const int32_t *__restrict__ sort
     }
 }
 
+// trips from the canonical order (sorted by root) into the order of the root slots of the current grouping
+__global__ void regroup_trips_kernel(int64_t T, const u32 *__restrict__ trip_root0, const int32_t *__restrict__ trip_target0,
+                                     const int64_t *__restrict__ root_off0, const u32 *__restrict__ slot_of,
+                                     const int64_t *__restrict__ new_start, u32 *__restrict__ trip_root, int32_t *__restrict__ trip_target)
+{
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < T; t += (int64_t)gridDim.x * blockDim.x) {
+        const u32 r = trip_root0[t];
+        const int64_t dst = new_start[r] + (t - root_off0[r]);
+        trip_root[dst] = slot_of[r];
+        trip_target[dst] = trip_target0[t];
+    }
+}
+
 // x[i] = table[x[i]]
 __global__ void gather_u32_kernel(int64_t n, u32 *__restrict__ x, const u32 *__restrict__ table)
 {

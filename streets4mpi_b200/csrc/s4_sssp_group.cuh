@@ -35,8 +35,8 @@ struct GroupParams {
     const Arc *arcs;        // A
     u64 *pool;              // first group slot of this launch
     size_t slot_stride;     // words per group slot = V * RW
-    const int32_t *roots;   // roots of this batch; group g owns roots [g*K, min(n_roots, (g+1)*K))
-    int n_roots;
+    const int32_t *roots;   // root slots of this batch; group g owns slots [g*K, (g+1)*K), -1 = empty (always at the end of a group)
+    int n_roots;            // slots, a multiple of K unless the caller hands in a plain list of roots
     int n_groups;
     u32 V;
     u32 *work_counter;      // zeroed before launch
@@ -217,7 +217,11 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024
         const int gi = s_group;
         if (gi >= p.n_groups) break;
         u64 *rows = p.pool + (size_t)gi * p.slot_stride;
-        const int k_live = min(K, p.n_roots - gi * K);          // trees of this group (the last group may be partial)
+        int k_live = 0;                                         // trees of this group: the slots holding a root
+        {
+            const int k_max = min(K, p.n_roots - gi * K);
+            for (int k = 0; k < k_max; ++k) k_live += p.roots[gi * K + k] >= 0 ? 1 : 0;
+        }
 
         // ---- fill the slot: +inf distances, meta = 0 (16-byte streaming stores)
         {
