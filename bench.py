@@ -43,6 +43,9 @@ WORKLOADS = {
     "grid256": (256, 256, 100_000),           # quick functional run
     "cfg4_planar5m": (0, 5_000_000, 10_000_000),   # BASELINE.json configs[3] (adaptation every 5 days)
     "planar200k": (0, 200_000, 200_000),
+    "planar1m": (0, 1_000_000, 1_000_000),          # tortuous stress case (no through roads)
+    "cfg4_road5m": (-1, 5_000_000, 10_000_000),     # BASELINE.json configs[3] with a speed hierarchy (synth.road_arrays)
+    "road1m": (-1, 1_000_000, 1_000_000),
 }
 
 
@@ -65,10 +68,18 @@ def make_workload(name, world, scaling="strong"):
         trips_total = TRIPS_OVERRIDE
     if scaling == "weak":
         trips_total *= world
-    arrays = synth.grid_arrays(rows, cols, seed=1) if rows else synth.planar_arrays(cols, seed=1)
+    arrays = graph_arrays(name)
     cats = synth.node_categories(arrays["node_ids"], seed=1, goal_fraction=0.02)
     per_rank = trips_total if scaling == "strong" else trips_total // world      # streets4mpi.py:69
     return arrays, cats, per_rank
+
+
+def graph_arrays(name):
+    from streets4mpi_b200 import synth
+    rows, cols, _ = WORKLOADS[name]
+    if rows > 0:
+        return synth.grid_arrays(rows, cols, seed=1)
+    return synth.planar_arrays(cols, seed=1) if rows == 0 else synth.road_arrays(cols, seed=1)
 
 
 def rank_trips(arrays, cats, per_rank, rank):
@@ -207,6 +218,26 @@ def _py_tree_worker(jobs):
     return time.perf_counter() - t0, hops
 
 
+_REF_PG = None         # python-graph stand-in of the same network (faithful variant), inherited by the forked workers
+
+
+def _py_faithful_worker(jobs):
+    """The reference's Dijkstra as python-graph ran it (recalled 1.8.x: sorted list + insort, dict-of-dict graph;
+    oracle/pygraph_standin.shortest_path), then the walk of simulation.py:78-88."""
+    from oracle import pygraph_standin as pg
+    hops = 0
+    t0 = time.perf_counter()
+    for origin, goals in jobs:
+        prev, _dist = pg.shortest_path(_REF_PG, origin)
+        for goal in goals:
+            if goal in prev:
+                cur = goal
+                while cur != origin:
+                    cur = prev[cur]
+                    hops += 1
+    return time.perf_counter() - t0, hops
+
+
 def reference_arm(args):
     """--impl reference: the reference's CPU path.  The reference itself (Python 2 + python-graph +
     mpi4py + imposm) cannot run in this image (DESIGN.md 'Oracle'), so this times the oracle port: a
@@ -237,6 +268,37 @@ def reference_arm(args):
             if s >= args.warmup:
                 times.append(dt)
                 trips_done.append(int(sum(off[i + 1] - off[i] for i in sel)))
+    # the labelled *faithful* variant: python-graph's own data structures and queue discipline
+    faithful = None
+    if args.faithful_trees_per_core > 0:
+        from oracle import pygraph_standin as pg
+        global _REF_PG
+        t0 = time.perf_counter()
+        gobj = pg.graph()
+        for n_ in range(V):
+            gobj.add_node(n_)
+        w_street = w.tolist()
+        for s_, (a_, b_) in enumerate(zip(arrays["u"].tolist(), arrays["v"].tolist())):
+            if a_ != b_ and not gobj.has_edge((a_, b_)):
+                gobj.add_edge((a_, b_), wt=w_street[s_])
+        build_s = time.perf_counter() - t0
+        _REF_PG = gobj
+        workers = min(cores, 8)
+        n_f = args.faithful_trees_per_core * workers
+        sel = list(range(n_f))
+        jobs = [(int(roots[i]), tg[off[i]:off[i + 1]].tolist()) for i in sel]
+        with mp.get_context("fork").Pool(workers) as pool:
+            t0 = time.perf_counter()
+            pool.map(_py_faithful_worker, [jobs[c::workers] for c in range(workers)])
+            dt = time.perf_counter() - t0
+        f_trips = int(sum(off[i + 1] - off[i] for i in sel))
+        faithful = {"value": f_trips / dt, "unit": "trips/s", "cores": workers, "kind": "port",
+                    "trees_per_sec": n_f / dt, "graph_build_seconds": build_s,
+                    "sample": "%d distinct origins (%d per process, %d processes): sorted-list insort Dijkstra on a dict-of-dict "
+                              "graph (oracle/pygraph_standin.shortest_path, the recalled python-graph 1.8.x algorithm), %.1f s"
+                              % (n_f, args.faithful_trees_per_core, workers, dt)}
+        _REF_PG = None
+        del gobj
     total_t = sum(times)
     value = sum(trips_done) / total_t
     sample = ("%d distinct origins per step (%d per core) of %d; full day extrapolates linearly in the number of "
@@ -248,7 +310,9 @@ def reference_arm(args):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload + ": " + workload_text(args.workload), "root_mode": "origin (reference grouping)",
                    "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "trips/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "trips/s", "cores": cores, "kind": "port", "sample": sample,
+                         "variant": "optimistic: heapq Dijkstra on flat lists (same trees as the faithful variant)"},
+        "faithful_variant": faithful,
         "e2e": {"value": value, "unit": "trips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -258,6 +322,10 @@ def reference_arm(args):
 def workload_text(name):
     rows, cols, trips = WORKLOADS[name]
     trips = TRIPS_OVERRIDE or trips
+    if rows < 0:
+        return ("synthetic road-like graph with a speed hierarchy (thinned jittered lattice, arterials every 16 and motorways "
+                "every 128 junctions, V=%d, mean degree 2.6), %d trips/day, goals = 2%% node sample, BASELINE.json "
+                "configs[3] shape" % (cols, trips))
     if not rows:
         return ("synthetic random planar road graph (thinned Delaunay, V=%d, S=%d, A=%d), %d trips/day, goals = 2%% node "
                 "sample, BASELINE.json configs[3] shape" % (cols, int(1.2 * cols), int(2.4 * cols), trips))
@@ -315,18 +383,30 @@ def gpu_arm(args):
         dev.set_option(k, float(v))
     settings["logging"] = None
 
+    if world > 1:
+        distributed.init(dev)          # the library's own NCCL communicator (s4_comm_init): the daily exchange runs there
     arrays, cats, per_rank = make_workload(args.workload, world, args.scaling)
+    net = synth.network_from(arrays)
+    curve = net.flat().locality_rank()
+
+    def strong_share(o_all, g_all, mode_in):
+        # one virtual rank for the whole job: its trees, sorted along the Hilbert curve, are cut into one contiguous
+        # run per GPU (neighbouring roots stay together: the SSSP kernel runs groups of neighbouring trees)
+        flat0 = net.flat()
+        order = None if curve is None else np.asarray(curve)
+        od, gd = flat0.dense(o_all), flat0.dense(g_all)
+        od, gd, forced_mode = distributed.partition_by_root(od, gd, rank, world, mode_in, order=order)
+        return flat0.node_ids[od], flat0.node_ids[gd], forced_mode
+
     if args.scaling == "strong":
-        # one virtual rank for the whole job: rank 0's trip stream and jam tolerance, trees dealt to the GPUs
         o, g, jam = rank_trips(arrays, cats, per_rank, 0)
-        o, g, forced = distributed.partition_by_root(o, g, rank, world, device_settings["root_mode"])
+        o, g, forced = strong_share(o, g, device_settings["root_mode"])
         device_settings["root_mode"] = forced
         job_trips = per_rank
         per_rank = len(o)
     else:
         o, g, jam = rank_trips(arrays, cats, per_rank, rank)
         job_trips = per_rank * world
-    net = synth.network_from(arrays)
     t0 = time.perf_counter()
     sim = Simulation(net, TripTable(o, g), jam, lambda *a: None, device=dev)
     dev.sync()
@@ -369,6 +449,8 @@ def gpu_arm(args):
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     c = sim.counters()
+    # the state after warm-up + K days: uint32 sums are exact, so in strong mode these do not depend on N
+    load_hash, cum_hash = sim._sim.load_hash()
     t_ms = torch.tensor([ms], dtype=torch.float64, device="cuda:%d" % local)
     agg = torch.tensor([c["sssp_instances"], c["arcs_algorithmic"], c["nodes_algorithmic"], c["trips_routed"],
                         c["kernel_launches"], c["hops"], c["arcs_relaxed"]], dtype=torch.float64, device="cuda:%d" % local)
@@ -389,7 +471,7 @@ def gpu_arm(args):
         with torch.cuda.stream(stream):
             sim.step()                                      # uploads what the driver assigned yesterday (H2D 8*S)
             local_load = sim.traffic_load                   # D2H 4*S -> array('I')
-            total = distributed.allreduce_array_I(local_load) if world > 1 else local_load   # :97-98
+            total = distributed.allreduce_array_I(local_load, device=dev) if world > 1 else local_load   # :97-98
             sim.traffic_load = total                        # :99
             sim.cumulative_traffic_load = merge_arrays((total, sim.cumulative_traffic_load))   # :100
     barrier()
@@ -410,6 +492,91 @@ def gpu_arm(args):
     barrier()
     cs = sim.counters()
     dev.set_option("lanes", 2)
+
+    # ---- secondary measurements: every number the design notes quote gets a driver-run twin (a few seconds each)
+    peak_gbs, _ = measured_peak()
+
+    def measured_days(sim_x, days=2, warm=1):
+        """{ms_per_day, trips/s ...} of `days` resident days (device events, max over ranks) + the SSSP kernel's
+        roofline fraction from one more strictly serial day."""
+        def one():
+            with torch.cuda.stream(stream):
+                sim_x.step()
+                sim_x.exchange()
+        for _ in range(warm):
+            one()
+        barrier()
+        sim_x._sim.reset_counters()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            a.record(stream)
+            for _ in range(days):
+                one()
+            b.record(stream)
+        barrier()
+        t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device="cuda:%d" % local)
+        cx = sim_x.counters()
+        tot = torch.tensor([cx["trips_routed"], cx["sssp_instances"], cx["hops"]], dtype=torch.float64, device="cuda:%d" % local)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        ms_day = float(t.item()) / days
+        trips_d, trees_d, hops_d = [float(x) / days for x in tot.tolist()]
+        dev.set_option("lanes", 1)
+        sim_x._sim.reset_counters()
+        one()
+        barrier()
+        cy = sim_x.counters()
+        dev.set_option("lanes", 2)
+        algb = 20.0 * cy["arcs_algorithmic"] + 20.0 * cy["nodes_algorithmic"]
+        frac = algb / (cy["ms_sssp"] * 1e-3) / 1e9 / peak_gbs if cy["ms_sssp"] > 0 else None
+        return {"ms_per_day": ms_day, "trips_per_sec": trips_d / (ms_day * 1e-3), "trees_per_day": trees_d,
+                "trees_per_sec": trees_d / (ms_day * 1e-3), "hops_per_trip": hops_d / max(1.0, trips_d),
+                "sssp_roofline_frac_rank0": frac, "sssp_ms_serial_day_rank0": cy["ms_sssp"], "walk_ms_serial_day_rank0": cy["ms_walk"],
+                "load_hash": "%016x" % sim_x._sim.load_hash()[0]}
+
+    secondary = {}
+    saved_mode = device_settings["root_mode"]
+    if not args.no_secondary:
+        if world == 1:
+            # the reference's own grouping, measured: one tree per distinct origin (simulation.py:71)
+            o2, g2, _ = rank_trips(arrays, cats, args.origin_rooted_trips, 0)
+            device_settings["root_mode"] = 0
+            sim_o = Simulation(net, TripTable(o2, g2), jam, lambda *a: None, device=dev)
+            secondary["origin_rooted_measured"] = dict(measured_days(sim_o), trips_per_day=len(o2), root_mode="origin",
+                                                       distinct_origins=int(sim_o._sim.n_roots))
+            sim_o._sim.close()
+        if world > 1:
+            # the reference's mpiexec -n N semantics: every rank its own trips (1/N of the day) and jam tolerance
+            o3, g3, jam3 = rank_trips(arrays, cats, job_trips // world if args.scaling == "strong" else per_rank, rank)
+            device_settings["root_mode"] = {"origin": 0, "goal": 1, "auto": 2}[args.root_mode]
+            sim_r = Simulation(net, TripTable(o3, g3), jam3, lambda *a: None, device=dev)
+            secondary["ranks_mode"] = dict(measured_days(sim_r), trips_per_day_per_rank=len(o3),
+                                           note="per-GPU virtual ranks with their own jam tolerance (streets4mpi.py:50-51,69,78): "
+                                                "every rank needs its own trees")
+            sim_r._sim.close()
+        if world == 8 or args.north_star:
+            # BASELINE.json north_star: a day with 10 M trips on the ~4 M-arc graph
+            o4, g4, jam4 = rank_trips(arrays, cats, 10_000_000, 0)
+            o4, g4, forced4 = strong_share(o4, g4, {"origin": 0, "goal": 1, "auto": 2}[args.root_mode])
+            device_settings["root_mode"] = forced4
+            sim_n = Simulation(net, TripTable(o4, g4), jam4, lambda *a: None, device=dev)
+            secondary["north_star_10M"] = dict(measured_days(sim_n), trips_per_day=10_000_000, gpus=world)
+            sim_n._sim.close()
+        if world == 1:
+            for wname in args.extra_graphs.split(","):
+                if not wname:
+                    continue
+                arr_x = graph_arrays(wname)
+                cats_x = synth.node_categories(arr_x["node_ids"], seed=1, goal_fraction=0.02)
+                net_x = synth.network_from(arr_x)
+                ox, gx, jx = rank_trips(arr_x, cats_x, WORKLOADS[wname][2], 0)
+                device_settings["root_mode"] = {"origin": 0, "goal": 1, "auto": 2}[args.root_mode]
+                sim_x = Simulation(net_x, TripTable(ox, gx), jx, lambda *a: None, device=dev)
+                secondary[wname + "_day"] = dict(measured_days(sim_x), workload=workload_text(wname))
+                sim_x._sim.close()
+                net_x._device_graph = None
+    device_settings["root_mode"] = saved_mode
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -442,9 +609,12 @@ def gpu_arm(args):
                                          "strong": "one virtual rank, its trees dealt round-robin to the GPUs",
                                          "ranks": "the day's trips divided over per-GPU virtual ranks"}[args.scaling],
                        "root_mode": "%s (trees per day and GPU: %d)" % (mode, sim._sim.n_roots),
-                       "virtual_ranks": world, "construction_every": args.construction_every,
+                       "virtual_ranks": 1 if args.scaling == "strong" else world, "construction_every": args.construction_every,
                        "l2": "inputs larger than L2 (per-tree distance arrays, 8 B x V x trees in flight >> 126 MB)",
                        "options": args.options or "defaults"},
+            "load_hash": "%016x" % load_hash, "cumulative_hash": "%016x" % cum_hash,
+            "hash_note": "FNV-1a of traffic_load / cumulative_traffic_load (uint32[S]) after warm-up + steps days; "
+                         "identical for every N in strong mode",
             "gteps": arcs_alg / (ms_max * 1e-3) / 1e9,
             "sssp_trees_per_sec": trees / (ms_max * 1e-3),
             "relaxations_per_algorithmic_arc": arcs_rel / max(1.0, arcs_alg),
@@ -454,6 +624,7 @@ def gpu_arm(args):
                 "distinct_origins_rank0": int(np.unique(o).size),
                 "trips_per_sec": trees / (ms_max * 1e-3) * per_rank / max(1, int(np.unique(o).size)),
                 "note": "root_mode=origin needs one tree per distinct origin instead of per distinct goal"},
+            "secondary": secondary,
             "hops_per_trip": hops / max(1.0, trips),
             "kernel_ms_serial_day": {"weights": cs["ms_weights"], "sssp": cs["ms_sssp"], "walk": cs["ms_walk"],
                                      "sssp_share": cs["ms_sssp"] / serial_total if serial_total else None,
@@ -497,6 +668,12 @@ def main():
                     help="weak: the workload's day per GPU (one virtual rank each); strong: one virtual rank, trees "
                          "dealt to the GPUs; ranks: the day's trips divided over per-GPU virtual ranks")
     ap.add_argument("--construction-every", type=int, default=0, help="road adaptation every N days (0 = never)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary measurements (origin-rooted day, "
+                    "per-rank jam tolerances, north-star day, road-like graphs)")
+    ap.add_argument("--origin-rooted-trips", type=int, default=30000)
+    ap.add_argument("--north-star", action="store_true", help="measure the 10 M-trip day at any GPU count (default: at 8)")
+    ap.add_argument("--extra-graphs", default="road1m,planar1m", help="workloads measured as secondary days at N=1")
+    ap.add_argument("--faithful-trees-per-core", type=int, default=1)
     args = ap.parse_args()
     global TRIPS_OVERRIDE
     TRIPS_OVERRIDE = args.trips

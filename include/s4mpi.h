@@ -121,6 +121,22 @@ int s4_ctx_get_option(s4_ctx *ctx, const char *key, double *value);
 /* name, SM count, bytes of HBM; name_out may be NULL */
 int s4_ctx_device_info(s4_ctx *ctx, char *name_out, int name_cap, int *sm_count, uint64_t *hbm_bytes);
 
+/* ---- rank-level exchange (streets4mpi.py:44-46, :97-98) --------------------------------------------------
+ * One s4_ctx = one MPI rank of the reference.  The collective is NCCL's all-reduce over NVLink, bound at run time
+ * to the libnccl the process already holds (torch's under Python; else $S4MPI_NCCL_LIB or libnccl.so.2), so a
+ * non-Python host gets the exchange from this library alone:
+ *     rank 0:      s4_comm_unique_id(id)   -> ship the 128 bytes to the other ranks (any transport)
+ *     every rank:  s4_comm_init(ctx, nranks, rank, id)              (mpi4py: COMM_WORLD, Get_rank, Get_size)
+ *     every day:   s4_sim_step(sim); s4_sim_exchange(sim);          (communicator.Allreduce(..., op=MPI.SUM))
+ * nranks == 1 needs no id and no NCCL (the reference started without mpiexec, README.md:73-80). */
+int s4_comm_unique_id(void *id_out_128_bytes);
+int s4_comm_init(s4_ctx *ctx, int nranks, int rank, const void *unique_id_128_bytes);
+int s4_comm_free(s4_ctx *ctx);
+int s4_comm_size(s4_ctx *ctx, int *nranks, int *rank);
+/* communicator.Allreduce(local, total, op=MPI.SUM) for a driver that keeps `traffic_load` in a host array
+ * (streets4mpi.py:97-98 literally): in place on inout[n], through a pinned staging buffer. */
+int s4_comm_allreduce_host(s4_ctx *ctx, uint32_t *inout, int64_t n);
+
 /* ---- graph (streetnetwork.py:35-57, 113-125) ------------------------------ */
 /* Street i joins u[i] and v[i] (either orientation, the graph is undirected:
  * streetnetwork.py:24,37), has length[i] metres and speed limit max_speed[i]
@@ -182,6 +198,13 @@ int s4_sim_load_add(s4_sim *dst, s4_sim *src);
 int s4_sim_load_copy(s4_sim *dst, s4_sim *src);
 /* streets4mpi.py:100 + utils.py:26-34: cumulative = load + (cumulative or 0) */
 int s4_sim_commit_total(s4_sim *sim);
+/* streets4mpi.py:97-100 in one stream-ordered call: traffic_load = Allreduce(traffic_load, SUM) over the ranks of
+ * s4_comm_init (ncclAllReduce, ncclUint32, in place on the device, no host synchronisation), then
+ * cumulative = traffic_load + (cumulative or 0).  With one rank it is s4_sim_commit_total. */
+int s4_sim_exchange(s4_sim *sim);
+/* 64-bit FNV-1a of traffic_load and of cumulative_traffic_load (0 when None); either pointer may be NULL.
+ * uint32 sums are exact, so the hashes of a day do not depend on how its trips were partitioned over GPUs. */
+int s4_sim_load_hash(s4_sim *sim, uint64_t *load_hash, uint64_t *cumulative_hash);
 /* `simulation.cumulative_traffic_load`: *is_none = 1 when it is None */
 int s4_sim_get_cumulative(s4_sim *sim, uint32_t *out, int *is_none);
 int s4_sim_set_cumulative(s4_sim *sim, const uint32_t *in_or_null);

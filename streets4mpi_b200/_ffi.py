@@ -54,6 +54,11 @@ SIGNATURES = {
     "s4_ctx_set_option": (C.c_int, [_vp, C.c_char_p, C.c_double]),
     "s4_ctx_get_option": (C.c_int, [_vp, C.c_char_p, _f64p]),
     "s4_ctx_device_info": (C.c_int, [_vp, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_uint64)]),
+    "s4_comm_unique_id": (C.c_int, [_vp]),
+    "s4_comm_init": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "s4_comm_free": (C.c_int, [_vp]),
+    "s4_comm_allreduce_host": (C.c_int, [_vp, _u32p, C.c_int64]),
+    "s4_comm_size": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "s4_graph_upload": (C.c_int, [_vp, C.c_int32, C.c_int64, _i32p, _i32p, _f64p, _i32p, _i32p, C.POINTER(_vp)]),
     "s4_graph_free": (C.c_int, [_vp]),
     "s4_graph_dims": (C.c_int, [_vp, C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
@@ -73,6 +78,8 @@ SIGNATURES = {
     "s4_sim_load_add": (C.c_int, [_vp, _vp]),
     "s4_sim_load_copy": (C.c_int, [_vp, _vp]),
     "s4_sim_commit_total": (C.c_int, [_vp]),
+    "s4_sim_exchange": (C.c_int, [_vp]),
+    "s4_sim_load_hash": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "s4_sim_get_cumulative": (C.c_int, [_vp, _u32p, C.POINTER(C.c_int)]),
     "s4_sim_set_cumulative": (C.c_int, [_vp, _u32p]),
     "s4_sim_road_construction": (C.c_int, [_vp, _u8p]),

@@ -9,6 +9,8 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
@@ -98,7 +100,24 @@ struct s4_ctx {
     cudaEvent_t sssp_done[2] = {nullptr, nullptr}, walk_done[2] = {nullptr, nullptr};
     cudaDeviceProp prop;
     Options opt;
+    void *nccl_comm = nullptr;      // ncclComm_t of the rank-level exchange (s4_comm_init), or null: single rank
+    void *stage_host = nullptr;     // pinned staging buffer + device scratch of s4_comm_allreduce_host
+    void *stage_dev = nullptr;
+    size_t stage_bytes = 0;
+    int comm_ranks = 1, comm_rank = 0;
 };
+
+// NCCL entry points, bound at run time (see "rank-level exchange" below)
+struct NcclId { char internal[128]; };
+struct NcclApi {
+    void *handle = nullptr;
+    int (*GetUniqueId)(NcclId *) = nullptr;
+    int (*CommInitRank)(void **, int, NcclId, int) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
 
 template <typename T>
 struct DevBuf {
@@ -260,6 +279,9 @@ static void ctx_unref(s4_ctx *ctx)
 {
     if (--ctx->refs > 0) return;
     cudaSetDevice(ctx->device);
+    if (ctx->nccl_comm && g_nccl.CommDestroy) { cudaStreamSynchronize(ctx->stream); g_nccl.CommDestroy(ctx->nccl_comm); }
+    if (ctx->stage_host) cudaFreeHost(ctx->stage_host);
+    if (ctx->stage_dev) cudaFree(ctx->stage_dev);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     if (ctx->walk_stream) cudaStreamDestroy(ctx->walk_stream);
     for (int i = 0; i < 2; ++i) {
@@ -350,6 +372,116 @@ extern "C" int s4_ctx_device_info(s4_ctx *ctx, char *name_out, int name_cap, int
     if (name_out && name_cap > 0) snprintf(name_out, (size_t)name_cap, "%s", ctx->prop.name);
     if (sm_count) *sm_count = ctx->prop.multiProcessorCount;
     if (hbm_bytes) *hbm_bytes = (uint64_t)ctx->prop.totalGlobalMem;
+    return S4_OK;
+}
+
+// ---------------------------------------------------------------------------
+// rank-level exchange (streets4mpi.py:44-46, :97-98): NCCL, bound at run time.
+// A process must hold ONE NCCL: under torch that is the libnccl torch already loaded (dlopen RTLD_NOLOAD finds
+// it), otherwise $S4MPI_NCCL_LIB or the system libnccl.so.2.  Only the five entry points below are used; their
+// signatures and the two enum values are NCCL's stable ABI (nccl.h: ncclUint32 = 3, ncclSum = 0, 128-byte id).
+// ---------------------------------------------------------------------------
+static int nccl_load()
+{
+    if (g_nccl.handle) return S4_OK;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);           // the one this process already has (torch)
+    const char *env = getenv("S4MPI_NCCL_LIB");
+    if (!h && env && *env) h = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return fail(S4_ERR_STATE, "NCCL is not available: %s", dlerror());
+    NcclApi a;
+    a.handle = h;
+    a.GetUniqueId = (int (*)(NcclId *))dlsym(h, "ncclGetUniqueId");
+    a.CommInitRank = (int (*)(void **, int, NcclId, int))dlsym(h, "ncclCommInitRank");
+    a.CommDestroy = (int (*)(void *))dlsym(h, "ncclCommDestroy");
+    a.AllReduce = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))dlsym(h, "ncclAllReduce");
+    a.GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
+    if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllReduce || !a.GetErrorString)
+        return fail(S4_ERR_STATE, "libnccl lacks an entry point this library needs");
+    g_nccl = a;
+    return S4_OK;
+}
+
+#define NC(expr)                                                                                            \
+    do {                                                                                                    \
+        int r__ = (expr);                                                                                   \
+        if (r__ != 0) return fail(S4_ERR_CUDA, "%s:%d %s -> NCCL: %s", __FILE__, __LINE__, #expr, g_nccl.GetErrorString(r__)); \
+    } while (0)
+
+extern "C" int s4_comm_unique_id(void *id_out)
+{
+    CHECK_ARG(id_out, "s4_comm_unique_id: NULL argument");
+    int rc = nccl_load();
+    if (rc) return rc;
+    NcclId id;
+    NC(g_nccl.GetUniqueId(&id));
+    memcpy(id_out, &id, sizeof id);
+    return S4_OK;
+}
+
+extern "C" int s4_comm_init(s4_ctx *ctx, int nranks, int rank, const void *unique_id)
+{
+    CHECK_ARG(ctx && nranks >= 1 && rank >= 0 && rank < nranks, "s4_comm_init: bad argument");
+    CHECK_ARG(nranks == 1 || unique_id, "s4_comm_init: unique_id is NULL");
+    if (ctx->nccl_comm) return fail(S4_ERR_STATE, "s4_comm_init: this context already has a communicator");
+    ctx->comm_ranks = nranks;
+    ctx->comm_rank = rank;
+    if (nranks == 1) return S4_OK;                                  // the reference without mpiexec: nothing to exchange
+    int rc = nccl_load();
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    NcclId id;
+    memcpy(&id, unique_id, sizeof id);
+    NC(g_nccl.CommInitRank(&ctx->nccl_comm, nranks, id, rank));
+    return S4_OK;
+}
+
+extern "C" int s4_comm_free(s4_ctx *ctx)
+{
+    CHECK_ARG(ctx, "s4_comm_free: ctx is NULL");
+    if (ctx->nccl_comm) {
+        CU(cudaSetDevice(ctx->device));
+        CU(cudaStreamSynchronize(ctx->stream));
+        NC(g_nccl.CommDestroy(ctx->nccl_comm));
+        ctx->nccl_comm = nullptr;
+    }
+    ctx->comm_ranks = 1;
+    ctx->comm_rank = 0;
+    return S4_OK;
+}
+
+// communicator.Allreduce(local, total, op=MPI.SUM) for a driver that keeps traffic_load on the host
+// (streets4mpi.py:97-98 as written): pinned staging, H2D, ncclAllReduce, D2H.  In place on `inout`.
+extern "C" int s4_comm_allreduce_host(s4_ctx *ctx, uint32_t *inout, int64_t n)
+{
+    CHECK_ARG(ctx && n >= 0 && (n == 0 || inout), "s4_comm_allreduce_host: bad argument");
+    if (ctx->comm_ranks <= 1 || n == 0) return S4_OK;
+    if (!ctx->nccl_comm) return fail(S4_ERR_STATE, "s4_comm_allreduce_host: %d ranks but no communicator (s4_comm_init)", ctx->comm_ranks);
+    CU(cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)n * sizeof(uint32_t);
+    if (bytes > ctx->stage_bytes) {
+        if (ctx->stage_host) cudaFreeHost(ctx->stage_host);
+        if (ctx->stage_dev) cudaFree(ctx->stage_dev);
+        ctx->stage_host = ctx->stage_dev = nullptr;
+        ctx->stage_bytes = 0;
+        CU(cudaHostAlloc(&ctx->stage_host, bytes, cudaHostAllocDefault));
+        CU(cudaMalloc(&ctx->stage_dev, bytes));
+        ctx->stage_bytes = bytes;
+    }
+    memcpy(ctx->stage_host, inout, bytes);
+    CU(cudaMemcpyAsync(ctx->stage_dev, ctx->stage_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    NC(g_nccl.AllReduce(ctx->stage_dev, ctx->stage_dev, (size_t)n, /*ncclUint32*/ 3, /*ncclSum*/ 0, ctx->nccl_comm, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->stage_host, ctx->stage_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    memcpy(inout, ctx->stage_host, bytes);
+    return S4_OK;
+}
+
+extern "C" int s4_comm_size(s4_ctx *ctx, int *nranks, int *rank)
+{
+    CHECK_ARG(ctx, "s4_comm_size: ctx is NULL");
+    if (nranks) *nranks = ctx->comm_ranks;
+    if (rank) *rank = ctx->comm_rank;
     return S4_OK;
 }
 
@@ -1546,6 +1678,54 @@ extern "C" int s4_sim_commit_total(s4_sim *sim)
         }
     }
     sim->has_cum = true;
+    return S4_OK;
+}
+
+// streets4mpi.py:97-100 in one call: total = Allreduce(local, SUM) in place on the device-resident counters
+// (stream-ordered behind the day's kernels, no host synchronisation), then cumulative = total + (cumulative or 0).
+extern "C" int s4_sim_exchange(s4_sim *sim)
+{
+    CHECK_ARG(sim, "s4_sim_exchange: sim is NULL");
+    s4_ctx *ctx = sim->g->ctx;
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->comm_ranks > 1) {
+        if (!ctx->nccl_comm) return fail(S4_ERR_STATE, "s4_sim_exchange: %d ranks but no communicator (s4_comm_init)", ctx->comm_ranks);
+        if (sim->g->S > 0)
+            NC(g_nccl.AllReduce(sim->load.p, sim->load.p, (size_t)sim->g->S, /*ncclUint32*/ 3, /*ncclSum*/ 0, ctx->nccl_comm, ctx->stream));
+    }
+    return s4_sim_commit_total(sim);
+}
+
+// 64-bit FNV-1a over the little-endian bytes of traffic_load / cumulative_traffic_load: lets a driver compare whole
+// load vectors across runs and GPU counts without moving them (tests, bench lines).
+static uint64_t fnv1a(const uint32_t *v, int64_t n)
+{
+    uint64_t h = 1469598103934665603ull;
+    const unsigned char *b = reinterpret_cast<const unsigned char *>(v);
+    for (int64_t i = 0; i < n * 4; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+    return h;
+}
+
+extern "C" int s4_sim_load_hash(s4_sim *sim, uint64_t *load_hash, uint64_t *cumulative_hash)
+{
+    CHECK_ARG(sim, "s4_sim_load_hash: sim is NULL");
+    s4_ctx *ctx = sim->g->ctx;
+    CU(cudaSetDevice(ctx->device));
+    const int64_t S = sim->g->S;
+    std::vector<uint32_t> h((size_t)std::max<int64_t>(S, 1));
+    if (load_hash) {
+        if (S > 0) CU(cudaMemcpyAsync(h.data(), sim->load.p, (size_t)S * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        *load_hash = fnv1a(h.data(), S);
+    }
+    if (cumulative_hash) {
+        *cumulative_hash = 0;
+        if (sim->has_cum) {
+            if (S > 0) CU(cudaMemcpyAsync(h.data(), sim->cum.p, (size_t)S * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            *cumulative_hash = fnv1a(h.data(), S);
+        }
+    }
     return S4_OK;
 }
 

@@ -55,6 +55,31 @@ class Device(object):
         check(self.lib.s4_ctx_get_option(self._h, key.encode(), C.byref(v)))
         return v.value
 
+    # ---- rank-level exchange (NCCL inside the library, streets4mpi.py:44-46)
+    def comm_unique_id(self):
+        """128-byte NCCL id; rank 0 creates it and ships it to the other ranks."""
+        buf = C.create_string_buffer(128)
+        check(self.lib.s4_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, nranks, rank, unique_id=None):
+        buf = C.create_string_buffer(bytes(unique_id), 128) if unique_id is not None else None
+        check(self.lib.s4_comm_init(self._h, int(nranks), int(rank), buf))
+
+    def comm_free(self):
+        check(self.lib.s4_comm_free(self._h))
+
+    def comm_size(self):
+        n, r = C.c_int(), C.c_int()
+        check(self.lib.s4_comm_size(self._h, C.byref(n), C.byref(r)))
+        return n.value, r.value
+
+    def allreduce_host(self, arr_u32):
+        """In-place SUM all-reduce of a host uint32 array over the ranks of comm_init."""
+        a = as_array(arr_u32, np.uint32)
+        check(self.lib.s4_comm_allreduce_host(self._h, ptr(a, C.c_uint32), len(a)))
+        return a
+
     def info(self):
         name = C.create_string_buffer(256)
         sm = C.c_int()
@@ -245,6 +270,17 @@ class DeviceSim(object):
 
     def commit_total(self):
         check(self.lib.s4_sim_commit_total(self._h))
+
+    def exchange(self):
+        """streets4mpi.py:97-100 on the device: NCCL all-reduce over the ranks of Device.comm_init, then the
+        cumulative merge."""
+        check(self.lib.s4_sim_exchange(self._h))
+
+    def load_hash(self):
+        """(FNV-1a of traffic_load, FNV-1a of cumulative_traffic_load or 0)"""
+        a, b = C.c_uint64(), C.c_uint64()
+        check(self.lib.s4_sim_load_hash(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def get_cumulative(self):
         out = np.empty(self.S, dtype=np.uint32)

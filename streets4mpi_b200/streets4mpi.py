@@ -23,6 +23,11 @@ class Streets4MPI(object):
 
     def __init__(self):
         self.process_rank, number_of_processes = distributed.world()
+        if number_of_processes > 1:
+            # streets4mpi.py:44-46: join the job the launcher started (torchrun) and create the communicator of the
+            # daily exchange; a rank that skipped this would silently route on its partial load
+            from . import engine
+            self.process_rank, number_of_processes = distributed.init(engine.default_device())
 
         self.log("Welcome to Streets4MPI!")
         random.seed(distributed.rank_seed(settings["random_seed"], self.process_rank))      # :50-51

@@ -95,6 +95,45 @@ def ladder_arrays(rows, cols, seed=1, rung_fraction=0.2):
             "lon": cc.astype(np.float64), "lat": rr.astype(np.float64)}
 
 
+def road_arrays(n_nodes, seed=1, arterial_every=16, motorway_every=128, keep_local=0.62):
+    """City-scale road-like graph with a speed hierarchy, O(V) time and memory (BASELINE cfg4 shape).
+
+    A jittered rows x cols lattice of junctions.  Local streets (30 / 50 km/h) survive with probability
+    ``keep_local`` (dead ends and irregular blocks, mean degree ~2.6 like real road graphs); every
+    ``arterial_every``-th row and column is a complete arterial (70 / 100 km/h), every ``motorway_every``-th a
+    motorway (120 / 140 km/h), so the graph is connected along the arterial mesh and a trip uses O(sqrt(V)) hops
+    like on a real network -- unlike ``planar_arrays`` (spanning tree + shortest leftover Delaunay edges: no
+    through roads, tens of thousands of hops per trip), which stays available as the tortuous stress case.
+    Junctions cut off inside a block by the thinning keep their node ids; trips to them are skipped like any
+    unreachable goal (simulation.py:80).  Lengths are Euclidean on the jittered positions (metres, ~120 m spacing)."""
+    rng = np.random.default_rng(seed)
+    cols = int(np.ceil(np.sqrt(n_nodes)))
+    rows = int(np.ceil(n_nodes / cols))
+    n = rows * cols
+    ids = np.arange(n, dtype=np.int64)
+    rr, cc = np.divmod(ids, cols)
+    x = (cc + rng.uniform(-0.3, 0.3, n)) * 120.0
+    y = (rr + rng.uniform(-0.3, 0.3, n)) * 120.0
+
+    def level(line):            # 2 motorway, 1 arterial, 0 local
+        return np.where(line % motorway_every == motorway_every // 2, 2, np.where(line % arterial_every == arterial_every // 2, 1, 0))
+
+    hu = ids[cc != cols - 1]
+    h_lvl = level(hu // cols)                                   # a horizontal street belongs to its row
+    vu = ids[: n - cols]
+    v_lvl = level(vu % cols)                                    # a vertical street to its column
+    keep_h = (h_lvl > 0) | (rng.random(len(hu)) < keep_local)
+    keep_v = (v_lvl > 0) | (rng.random(len(vu)) < keep_local)
+    u = np.concatenate([hu[keep_h], vu[keep_v]])
+    v = np.concatenate([hu[keep_h] + 1, vu[keep_v] + cols])
+    lvl = np.concatenate([h_lvl[keep_h], v_lvl[keep_v]])
+    length = np.maximum(np.hypot(x[u] - x[v], y[u] - y[v]) * rng.uniform(1.0, 1.3, len(u)), 5.0)
+    ms = np.where(lvl == 2, rng.choice(np.array([120, 140], dtype=np.int32), len(u)),
+                  np.where(lvl == 1, rng.choice(np.array([70, 100], dtype=np.int32), len(u)),
+                           rng.choice(np.array([30, 50], dtype=np.int32), len(u), p=[0.6, 0.4]))).astype(np.int32)
+    return {"node_ids": ids, "u": u, "v": v, "length": length, "max_speed": ms, "lon": x, "lat": y}
+
+
 def network_from(arrays):
     return StreetNetwork.from_arrays(arrays["node_ids"], arrays["u"], arrays["v"], arrays["length"],
                                      arrays["max_speed"], arrays.get("lon"), arrays.get("lat"))
@@ -121,7 +160,8 @@ def trip_arrays(n_trips, origins, goals, seed):
 
 
 def parse_spec(spec):
-    """'synthetic:grid:ROWSxCOLS[:seed]', 'synthetic:planar:N[:seed]' or 'synthetic:ladder:ROWSxCOLS[:seed]' -> arrays"""
+    """'synthetic:grid:ROWSxCOLS[:seed]', 'synthetic:planar:N[:seed]', 'synthetic:road:N[:seed]' or
+    'synthetic:ladder:ROWSxCOLS[:seed]' -> arrays"""
     parts = spec.split(":")
     if len(parts) < 3 or parts[0] != "synthetic":
         raise ValueError("not a synthetic network spec: %r" % (spec,))
@@ -131,6 +171,8 @@ def parse_spec(spec):
         return grid_arrays(int(r), int(c), seed)
     if parts[1] == "planar":
         return planar_arrays(int(parts[2]), seed)
+    if parts[1] == "road":
+        return road_arrays(int(parts[2]), seed)
     if parts[1] == "ladder":
         r, c = parts[2].lower().split("x")
         return ladder_arrays(int(r), int(c), seed)
