@@ -606,7 +606,7 @@ def gpu_arm(args):
             "config": {"workload": args.workload + ": " + workload_text(args.workload),
                        "trips_per_day": {"per_gpu_rank0": per_rank, "job": job_trips},
                        "decomposition": {"weak": "one virtual rank (own trips, own jam tolerance) per GPU",
-                                         "strong": "one virtual rank, its trees dealt round-robin to the GPUs",
+                                         "strong": "one virtual rank; its trees, sorted along the Hilbert curve, cut into one contiguous run per GPU",
                                          "ranks": "the day's trips divided over per-GPU virtual ranks"}[args.scaling],
                        "root_mode": "%s (trees per day and GPU: %d)" % (mode, sim._sim.n_roots),
                        "virtual_ranks": 1 if args.scaling == "strong" else world, "construction_every": args.construction_every,
@@ -628,7 +628,7 @@ def gpu_arm(args):
             "hops_per_trip": hops / max(1.0, trips),
             "kernel_ms_serial_day": {"weights": cs["ms_weights"], "sssp": cs["ms_sssp"], "walk": cs["ms_walk"],
                                      "sssp_share": cs["ms_sssp"] / serial_total if serial_total else None,
-                                     "note": "one extra day with lanes=1 (no overlap), CUDA events per launch"},
+                                     "note": "one extra day with lanes=1 (separate kernels, no overlap), CUDA events per launch"},
             "roofline": {"bound": "hbm", "kernel": "sssp", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes / n_launch, "ms_per_launch": ms_launch,

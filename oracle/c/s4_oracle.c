@@ -116,33 +116,77 @@ static void dijkstra(int32_t V, const int64_t *row_ptr, const int32_t *col,
 }
 
 /*
- * Canonical predecessor of v given converged distances:
- *   min (u, street) over arcs (v,u) with fl(dist[u]+w) == dist[v] and
- *   (dist[u] < dist[v] or u < v); if that set is empty, over all equal-cost
- *   arcs with u != v.  Returns -1 if none.  *n_cand = size of the set used.
+ * Canonical predecessor of v given converged distances (same rule as oracle/port.py canonical_tree).
+ * Candidates: arcs (v,u), u != v, dist[u] finite, fl(dist[u]+w) == dist[v].
+ *   - some candidate strictly closer (dist[u] < dist[v]): min (u, street) among those;
+ *   - else v is on a plateau (zero / absorbed weights): breadth-first search over the plateau, candidates in
+ *     ascending (u, street) order, at most PLATEAU_MAX nodes, to the nearest node with a strictly closer
+ *     candidate (or the root); the first hop of that path.  Levels decrease along the chain: no cycles.
+ * Returns -1 if none.  *n_cand = number of candidates of v.
  */
-static int32_t canon_pred(int32_t v, const int64_t *row_ptr, const int32_t *col,
-                          const int32_t *arc_street, const double *w,
-                          const double *dist, int32_t *street_out, int *n_cand)
+#define PLATEAU_MAX 32
+
+/* smallest candidate of x that is > (after_u, after_s) in (u, street) order; closer_only: dist[u] < dist[x] */
+static int32_t next_cand(int32_t x, int32_t after_u, int32_t after_s, int closer_only, const int64_t *row_ptr,
+                         const int32_t *col, const int32_t *arc_street, const double *w, const double *dist,
+                         int32_t *street_out)
 {
-    double dv = dist[v];
-    int32_t best_u = -1, best_s = -1, loose_u = -1, loose_s = -1;
-    int ns = 0, nl = 0;
-    for (int64_t e = row_ptr[v]; e < row_ptr[v + 1]; ++e) {
+    double dx = dist[x];
+    int32_t best_u = -1, best_s = -1;
+    for (int64_t e = row_ptr[x]; e < row_ptr[x + 1]; ++e) {
         int32_t u = col[e], s = arc_street[e];
-        if (u == v) continue;
+        if (u == x) continue;
         double du = dist[u];
-        if (!(du + w[s] == dv)) continue;            /* inf+w == inf is excluded below */
-        if (isinf(du)) continue;
-        if (loose_u < 0 || u < loose_u || (u == loose_u && s < loose_s)) { loose_u = u; loose_s = s; }
-        ++nl;
-        if (du < dv || u < v) {
-            if (best_u < 0 || u < best_u || (u == best_u && s < best_s)) { best_u = u; best_s = s; }
-            ++ns;
-        }
+        if (isinf(du) || !(du + w[s] == dx)) continue;
+        if (closer_only && !(du < dx)) continue;
+        if (u < after_u || (u == after_u && s <= after_s)) continue;
+        if (best_u < 0 || u < best_u || (u == best_u && s < best_s)) { best_u = u; best_s = s; }
     }
-    if (best_u >= 0) { *street_out = best_s; if (n_cand) *n_cand = ns; return best_u; }
-    *street_out = loose_s; if (n_cand) *n_cand = nl; return loose_u;
+    *street_out = best_s;
+    return best_u;
+}
+
+static int32_t canon_pred_root(int32_t v, int32_t root, const int64_t *row_ptr, const int32_t *col,
+                               const int32_t *arc_street, const double *w,
+                               const double *dist, int32_t *street_out, int *n_cand)
+{
+    int32_t s = -1;
+    if (n_cand) {
+        int nc = 0;
+        int32_t cu = -1, cs = -1;
+        for (;;) { cu = next_cand(v, cu, cs, 0, row_ptr, col, arc_street, w, dist, &cs); if (cu < 0) break; ++nc; }
+        *n_cand = nc;
+    }
+    int32_t u = next_cand(v, -1, -1, 1, row_ptr, col, arc_street, w, dist, &s);
+    if (u >= 0) { *street_out = s; return u; }
+    /* plateau search */
+    int32_t seen[PLATEAU_MAX], first_u[PLATEAU_MAX], first_s[PLATEAU_MAX];
+    int n_seen = 1, head = 0;
+    seen[0] = v; first_u[0] = -1; first_s[0] = -1;
+    while (head < n_seen) {
+        int32_t x = seen[head];
+        int32_t cu = -1, cs = -1;
+        for (;;) {
+            cu = next_cand(x, cu, cs, 0, row_ptr, col, arc_street, w, dist, &cs);
+            if (cu < 0) break;
+            int dup = 0;
+            for (int k = 0; k < n_seen; ++k) if (seen[k] == cu) { dup = 1; break; }
+            if (dup) continue;
+            if (n_seen >= PLATEAU_MAX) { *street_out = -1; return -1; }
+            seen[n_seen] = cu;
+            first_u[n_seen] = head == 0 ? cu : first_u[head];
+            first_s[n_seen] = head == 0 ? cs : first_s[head];
+            int32_t dummy;
+            if (cu == root || next_cand(cu, -1, -1, 1, row_ptr, col, arc_street, w, dist, &dummy) >= 0) {
+                *street_out = first_s[n_seen];
+                return first_u[n_seen];
+            }
+            ++n_seen;
+        }
+        ++head;
+    }
+    *street_out = -1;
+    return -1;
 }
 
 /* streetnetwork.py:108-109: one tree.  pred[src] = -1, pred[unreachable] = -1,
@@ -160,7 +204,7 @@ int o_sssp(int32_t V, const int64_t *row_ptr, const int32_t *col,
         for (int32_t v = 0; v < V; ++v) {
             int32_t s; int nc = 0;
             if (v == src || isinf(dist_out[v])) { pred_out[v] = -1; if (tied_out) tied_out[v] = 0; continue; }
-            pred_out[v] = canon_pred(v, row_ptr, col, arc_street, w, dist_out, &s, &nc);
+            pred_out[v] = canon_pred_root(v, src, row_ptr, col, arc_street, w, dist_out, &s, &nc);
             if (tied_out) tied_out[v] = nc > 1;
         }
     }
@@ -205,7 +249,7 @@ static void *day_worker(void *arg)
             int64_t guard = 0;
             while (here != root) {                                           /* :83 */
                 int32_t s; int nc = 0;
-                int32_t nxt = canon_pred(here, j->row_ptr, j->col, j->arc_street, j->w, dist, &s, &nc);
+                int32_t nxt = canon_pred_root(here, root, j->row_ptr, j->col, j->arc_street, j->w, dist, &s, &nc);
                 if (nxt < 0 || ++guard > (int64_t)V) { ++j->stuck; break; }
                 if (nc > 1) tied = 1;
                 __atomic_fetch_add(&j->load[s], j->trip_volume, __ATOMIC_RELAXED);   /* :86-88 */

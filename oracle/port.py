@@ -141,16 +141,22 @@ class Network(object):
 # --------------------------------------------------------------------------
 # A4  canonical Dijkstra (tie rule of DESIGN.md / SURVEY 8(c))
 # --------------------------------------------------------------------------
+PLATEAU_MAX = 32     # nodes a plateau search may touch before the trip counts as stuck (same bound on the GPU)
+
+
 def canonical_tree(g, origin):
     """Dijkstra with strict ``<`` (distances equal python-graph's), then the
-    schedule-independent predecessor rule
+    schedule-independent predecessor rule.  Candidates of v are the neighbours u != v with
+    ``fl(dist[u] + w(u,v)) == dist[v]``:
 
-        pred[v] = min{ u in N(v) : fl(dist[u] + w(u,v)) == dist[v]
-                                   and (dist[u] < dist[v] or u < v) }
+    * if some candidate is strictly closer to the origin (``dist[u] < dist[v]``), the one with the smallest id;
+    * otherwise v sits on a *plateau* (zero or absorbed weights: its distance is only reproduced by neighbours at
+      the same distance).  A breadth-first search over the plateau -- candidates in ascending id order, at most
+      ``PLATEAU_MAX`` nodes -- finds the nearest node that has a strictly closer candidate; pred[v] is the first
+      hop towards it.  Every step reduces the plateau level, so predecessor chains never cycle (a "smallest
+      equal-cost neighbour" rule can oscillate between two nodes of a zero-weight chain).
 
-    falling back to the smallest equal-cost neighbour when that set is empty
-    (only possible behind zero / absorbed weights).  Returns
-    ``(previous, dist, tied)``; ``tied`` = nodes with more than one candidate.
+    Returns ``(previous, dist, tied)``; ``tied`` = nodes with more than one candidate.
     """
     dist = {origin: 0}
     heap = [(0, origin)]
@@ -167,23 +173,45 @@ def canonical_tree(g, origin):
             if v not in dist or alt < dist[v]:
                 dist[v] = alt
                 heapq.heappush(heap, (alt, v))
+
+    def candidates(v):
+        dv = dist[v]
+        return sorted(set(u for u in g.neighbors(v)
+                          if u in dist and u != v and dist[u] + g.edge_weight((u, v)) == dv))
+
+    def closer(v):
+        return [u for u in candidates(v) if dist[u] < dist[v]]
+
     previous = {origin: None}
     tied = set()
-    for v, dv in dist.items():
+    for v in dist:
         if v == origin:
             continue
-        strict, loose = [], []
-        for u in g.neighbors(v):
-            if u not in dist or u == v:
-                continue
-            if dist[u] + g.edge_weight((u, v)) == dv:
-                loose.append(u)
-                if dist[u] < dv or u < v:
-                    strict.append(u)
-        cands = strict if strict else loose
-        previous[v] = min(cands)
-        if len(set(cands)) > 1:
+        cands = candidates(v)
+        near = [u for u in cands if dist[u] < dist[v]]
+        if len(cands) > 1:
             tied.add(v)
+        if near:
+            previous[v] = near[0]
+            continue
+        # plateau search
+        first = {v: None}
+        queue = [v]
+        found = None
+        while queue and found is None:
+            x = queue.pop(0)
+            for u in candidates(x):                     # all at dist[v]: x has no closer candidate
+                if u in first:
+                    continue
+                if len(first) >= PLATEAU_MAX:
+                    queue = []
+                    break
+                first[u] = u if x == v else first[x]
+                if u == origin or closer(u):
+                    found = first[u]
+                    break
+                queue.append(u)
+        previous[v] = found                              # None: stuck (plateau larger than the bound)
     return previous, dist, tied
 
 

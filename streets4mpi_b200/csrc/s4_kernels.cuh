@@ -604,52 +604,89 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024
 }
 
 // ---------------------------------------------------------------------------
-// Canonical predecessor of `cur` from converged distances, evaluated by the
-// lanes of one tile (lane k looks at arcs rb+k, rb+k+TILE, ...):
-//   min (id(u), street) over arcs (cur,u), u != cur, with fl(dist[u]+w) == dist[cur]
-//   and (dist[u] < dist[cur] or id(u) < id(cur)); if empty, over all equal-cost arcs.
-// id() is the caller's node id: the device numbers nodes along a space-filling
-// curve (locality), `orig` maps that numbering back so that the tie-break is the
-// one the host sees (nullptr = identical numbering).
-// Returns the packed key (id(u) << 32 | street), ~0 if there is none; *col_out is
-// the device number of the winner and *du_out its distance (valid on every lane).
+// Canonical predecessor of `cur` from converged distances (the rule of oracle/port.py canonical_tree and
+// oracle/c/s4_oracle.c canon_pred_root), evaluated by the lanes of one tile (lane k looks at arcs rb+k, rb+k+TILE, ...).
+// Candidates: arcs (cur,u), u != cur, dist[u] finite, fl(dist[u]+w) == dist[cur].
+//   - some candidate strictly closer to the root (dist[u] < dist[cur]): min (id(u), street) among those;
+//   - else `cur` sits on a plateau (zero / absorbed weights): bounded breadth-first search over the plateau to the
+//     nearest node that has a strictly closer candidate (or the root), first hop of that path (plateau_first_hop).
+// id() is the caller's node id: the device numbers nodes along a space-filling curve (locality), `orig` maps that
+// numbering back so that the tie-break is the one the host sees (nullptr = identical numbering).
+// Returns the packed key (id(u) << 32 | street), ~0 if there is none; *col_out is the device number of the winner
+// and *du_out its distance (valid on every lane).
 // ---------------------------------------------------------------------------
+static constexpr int kPlateauMax = 32;     // nodes a plateau search may touch (oracle: PLATEAU_MAX)
+
+// smallest candidate of x above `after` in (id(u), street) order (has_after = false: the smallest of all);
+// closer_only: dist[u] < dist[x].  Sequential over the CSR row: the slow path behind zero-weight streets.
+__device__ __noinline__ u64 next_candidate(const u32 *__restrict__ row_ptr, const Arc *__restrict__ arcs, const u32 *__restrict__ orig,
+                                           const u64 *dist, u32 stride, u32 x, bool has_after, u64 after, bool closer_only, u32 *col_out)
+{
+    const u64 dx = ld_dist(dist + (size_t)x * stride);
+    u64 best = ~0ull;
+    u32 bcol = 0;
+    for (u32 e = __ldg(row_ptr + x), re = __ldg(row_ptr + x + 1); e < re; ++e) {
+        const Arc a = ld_arc(arcs + e);
+        if (a.col == x) continue;
+        const u64 du = ld_dist(dist + (size_t)a.col * stride);
+        if (du >= kInfBits) continue;
+        if ((u64)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)du), a.w)) != dx) continue;
+        if (closer_only && !(du < dx)) continue;
+        const u64 key = ((u64)(orig ? __ldg(orig + a.col) : a.col) << 32) | a.street;
+        if (has_after && key <= after) continue;
+        if (key < best) { best = key; bcol = a.col; }
+    }
+    *col_out = bcol;
+    return best;
+}
+
+// every lane of the tile runs the same search on the same data (uniform, the loads broadcast)
+__device__ __noinline__ u64 plateau_first_hop(const u32 *__restrict__ row_ptr, const Arc *__restrict__ arcs, const u32 *__restrict__ orig,
+                                              const u64 *dist, u32 stride, u32 v, u32 root, u32 *col_out)
+{
+    u32 seen[kPlateauMax], first_col[kPlateauMax];
+    u64 first_key[kPlateauMax];
+    int n_seen = 1;
+    seen[0] = v; first_col[0] = 0u; first_key[0] = ~0ull;
+    for (int head = 0; head < n_seen; ++head) {
+        const u32 x = seen[head];
+        bool has = false;
+        u64 after = 0ull;
+        for (;;) {
+            u32 cu;
+            const u64 key = next_candidate(row_ptr, arcs, orig, dist, stride, x, has, after, false, &cu);
+            if (key == ~0ull) break;
+            has = true;
+            after = key;
+            bool dup = false;
+            for (int k = 0; k < n_seen; ++k) dup = dup || seen[k] == cu;
+            if (dup) continue;
+            if (n_seen >= kPlateauMax) { *col_out = 0u; return ~0ull; }
+            seen[n_seen] = cu;
+            first_key[n_seen] = head == 0 ? key : first_key[head];
+            first_col[n_seen] = head == 0 ? cu : first_col[head];
+            u32 dummy;
+            if (cu == root || next_candidate(row_ptr, arcs, orig, dist, stride, cu, false, 0ull, true, &dummy) != ~0ull) {
+                *col_out = first_col[n_seen];
+                return first_key[n_seen];
+            }
+            ++n_seen;
+        }
+    }
+    *col_out = 0u;
+    return ~0ull;
+}
+
 template <int TILE, bool WANT_ID>
 __device__ __forceinline__ u64 canonical_pred(const cg::thread_block_tile<TILE> &tile, const u32 *__restrict__ row_ptr,
                                               const Arc *__restrict__ arcs, const u32 *__restrict__ orig, const u64 *dist,
-                                              u32 stride, u32 cur, u64 dv, u32 *col_out, u64 *du_out)
+                                              u32 stride, u32 cur, u64 dv, u32 root, u32 *col_out, u64 *du_out)
 {
     const u32 rb = __ldg(row_ptr + cur), re = __ldg(row_ptr + cur + 1);
-    // pass 1: which arcs reproduce dist[cur] exactly?  Almost always exactly one (unique shortest path):
-    // then neither the ids nor the strict / loose distinction matter and no id lookup is needed.
-    u64 key1 = ~0ull, du1 = 0;
-    u32 col1 = 0, n_cand = 0;
-    for (u32 e = rb + tile.thread_rank(); tile.any(e < re); e += TILE) {
-        if (e < re) {
-            const Arc a = ld_arc(arcs + e);
-            if (a.col != cur) {
-                const u64 du = ld_dist(dist + (size_t)a.col * stride);
-                const u64 ndb = (u64)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)du), a.w));
-                if (du < kInfBits && ndb == dv) { ++n_cand; key1 = a.street; du1 = du; col1 = a.col; }
-            }
-        }
-    }
-    u32 total = n_cand;
-    for (int o = TILE / 2; o > 0; o >>= 1) total += tile.shfl_xor(total, o);
-    if (total == 1u) {
-        // broadcast the single candidate from the lane that holds it
-        const u32 src = (u32)__ffs((int)tile.ballot(n_cand != 0u)) - 1u;
-        const u32 street = tile.shfl((u32)key1, src);
-        *col_out = tile.shfl(col1, src);
-        *du_out = tile.shfl(du1, src);
-        const u32 id_u = !WANT_ID ? 0u : orig ? __ldg(orig + *col_out) : *col_out;     // the walk only needs the street
-        return ((u64)id_u << 32) | street;
-    }
-    if (total == 0u) { *du_out = 0; *col_out = 0; return ~0ull; }
-    // ties: the full rule on the caller's ids
-    const u32 id_cur = orig ? __ldg(orig + cur) : cur;
-    u64 strict = ~0ull, loose = ~0ull, du_s = 0, du_l = 0;
-    u32 col_s = 0, col_l = 0;
+    // pass 1: which arcs reproduce dist[cur] exactly, and from a strictly smaller distance?  Almost always exactly
+    // one (unique shortest path): then the ids do not matter and no id lookup is needed.
+    u64 du1 = 0;
+    u32 street1 = 0, col1 = 0, n_cand = 0, n_close = 0;
     for (u32 e = rb + tile.thread_rank(); tile.any(e < re); e += TILE) {
         if (e < re) {
             const Arc a = ld_arc(arcs + e);
@@ -657,27 +694,54 @@ __device__ __forceinline__ u64 canonical_pred(const cg::thread_block_tile<TILE> 
                 const u64 du = ld_dist(dist + (size_t)a.col * stride);
                 const u64 ndb = (u64)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)du), a.w));
                 if (du < kInfBits && ndb == dv) {
-                    const u32 id_u = orig ? __ldg(orig + a.col) : a.col;
-                    const u64 key = ((u64)id_u << 32) | a.street;
-                    if (key < loose) { loose = key; du_l = du; col_l = a.col; }
-                    if ((du < dv || id_u < id_cur) && key < strict) { strict = key; du_s = du; col_s = a.col; }
+                    ++n_cand;
+                    if (du < dv) { ++n_close; street1 = a.street; du1 = du; col1 = a.col; }
                 }
             }
         }
     }
-    // tile-wide minimum of both keys, carrying the winner's number and distance along
-    for (int o = TILE / 2; o > 0; o >>= 1) {
-        const u64 ks = tile.shfl_xor(strict, o), ds = tile.shfl_xor(du_s, o);
-        const u32 cs = tile.shfl_xor(col_s, o);
-        if (ks < strict) { strict = ks; du_s = ds; col_s = cs; }
-        const u64 kl = tile.shfl_xor(loose, o), dl = tile.shfl_xor(du_l, o);
-        const u32 cl = tile.shfl_xor(col_l, o);
-        if (kl < loose) { loose = kl; du_l = dl; col_l = cl; }
+    u32 total = n_cand | (n_close << 16);
+    for (int o = TILE / 2; o > 0; o >>= 1) total += tile.shfl_xor(total, o);
+    const u32 closer = total >> 16;
+    if (closer == 1u) {
+        // broadcast the single closer candidate from the lane that holds it
+        const u32 src = (u32)__ffs((int)tile.ballot(n_close != 0u)) - 1u;
+        const u32 street = tile.shfl(street1, src);
+        *col_out = tile.shfl(col1, src);
+        *du_out = tile.shfl(du1, src);
+        const u32 id_u = !WANT_ID ? 0u : orig ? __ldg(orig + *col_out) : *col_out;     // the walk only needs the street
+        return ((u64)id_u << 32) | street;
     }
-    if (strict != ~0ull) { *du_out = du_s; *col_out = col_s; return strict; }
-    *du_out = du_l;
-    *col_out = col_l;
-    return loose;
+    if ((total & 0xFFFFu) == 0u) { *du_out = 0; *col_out = 0; return ~0ull; }
+    if (closer == 0u) {
+        // plateau: every candidate is at dist[cur]
+        *du_out = dv;
+        return plateau_first_hop(row_ptr, arcs, orig, dist, stride, cur, root, col_out);
+    }
+    // several closer candidates: smallest (id, street)
+    u64 best = ~0ull, du_b = 0;
+    u32 col_b = 0;
+    for (u32 e = rb + tile.thread_rank(); tile.any(e < re); e += TILE) {
+        if (e < re) {
+            const Arc a = ld_arc(arcs + e);
+            if (a.col != cur) {
+                const u64 du = ld_dist(dist + (size_t)a.col * stride);
+                const u64 ndb = (u64)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)du), a.w));
+                if (du < dv && ndb == dv) {
+                    const u64 key = ((u64)(orig ? __ldg(orig + a.col) : a.col) << 32) | a.street;
+                    if (key < best) { best = key; du_b = du; col_b = a.col; }
+                }
+            }
+        }
+    }
+    for (int o = TILE / 2; o > 0; o >>= 1) {
+        const u64 kb = tile.shfl_xor(best, o), db = tile.shfl_xor(du_b, o);
+        const u32 cb = tile.shfl_xor(col_b, o);
+        if (kb < best) { best = kb; du_b = db; col_b = cb; }
+    }
+    *du_out = du_b;
+    *col_out = col_b;
+    return best;
 }
 
 // The same rule on the fixed-stride rows (ellw: first kEllWidth arcs of every node, lane k of the tile looks at slot
@@ -687,7 +751,7 @@ template <int TILE, bool WANT_ID>
 __device__ __forceinline__ u64 canonical_pred_ell(const cg::thread_block_tile<TILE> &tile, const Arc *__restrict__ ellw,
                                                   const u32 *__restrict__ row_ptr, const Arc *__restrict__ arcs,
                                                   const u32 *__restrict__ orig, const u64 *dist, u32 stride, u32 cur, u64 dv,
-                                                  u32 *col_out, u64 *du_out)
+                                                  u32 root, u32 *col_out, u64 *du_out)
 {
     static_assert(TILE >= kEllWidth, "one lane per slot");
     const u32 lane = tile.thread_rank();
@@ -695,7 +759,7 @@ __device__ __forceinline__ u64 canonical_pred_ell(const cg::thread_block_tile<TI
     a.col = cur; a.street = 0u; a.w = 0.0;
     if (lane < (u32)kEllWidth) a = ld_arc(ellw + (size_t)cur * kEllWidth + lane);
     if (tile.any(lane == 0u && (a.col & kOvfBit) != 0u))
-        return canonical_pred<TILE, WANT_ID>(tile, row_ptr, arcs, orig, dist, stride, cur, dv, col_out, du_out);
+        return canonical_pred<TILE, WANT_ID>(tile, row_ptr, arcs, orig, dist, stride, cur, dv, root, col_out, du_out);
     const u32 col = a.col;
     u64 du = 0;
     bool match = false;
@@ -704,39 +768,34 @@ __device__ __forceinline__ u64 canonical_pred_ell(const cg::thread_block_tile<TI
         const u64 ndb = (u64)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)du), a.w));
         match = du < kInfBits && ndb == dv;
     }
-    const u32 mm = tile.ballot(match);
-    if (mm == 0u) { *du_out = 0; *col_out = 0; return ~0ull; }
-    if ((mm & (mm - 1u)) == 0u) {
-        // exactly one arc reproduces dist[cur] (unique shortest path): no id lookup needed for the walk
-        const u32 src = (u32)__ffs((int)mm) - 1u;
+    const bool close = match && du < dv;
+    const u32 mc = tile.ballot(close);
+    if (mc != 0u && (mc & (mc - 1u)) == 0u) {
+        // exactly one arc reproduces dist[cur] from a smaller distance (unique shortest path): no id lookup needed
+        const u32 src = (u32)__ffs((int)mc) - 1u;
         const u32 street = tile.shfl(a.street, src);
         *col_out = tile.shfl(col, src);
         *du_out = tile.shfl(du, src);
         const u32 id_u = !WANT_ID ? 0u : orig ? __ldg(orig + *col_out) : *col_out;
         return ((u64)id_u << 32) | street;
     }
-    // ties: the full rule on the caller's ids
-    const u32 id_cur = orig ? __ldg(orig + cur) : cur;
-    u64 strict = ~0ull, loose = ~0ull, du_s = 0, du_l = 0;
-    u32 col_s = 0, col_l = 0;
-    if (match) {
-        const u32 id_u = orig ? __ldg(orig + col) : col;
-        const u64 key = ((u64)id_u << 32) | a.street;
-        loose = key; du_l = du; col_l = col;
-        if (du < dv || id_u < id_cur) { strict = key; du_s = du; col_s = col; }
+    if (mc == 0u) {
+        if (!tile.any(match)) { *du_out = 0; *col_out = 0; return ~0ull; }
+        *du_out = dv;                                                    // plateau
+        return plateau_first_hop(row_ptr, arcs, orig, dist, stride, cur, root, col_out);
     }
+    // several closer candidates: smallest (id, street)
+    u64 best = ~0ull, du_b = 0;
+    u32 col_b = 0;
+    if (close) { best = ((u64)(orig ? __ldg(orig + col) : col) << 32) | a.street; du_b = du; col_b = col; }
     for (int o = TILE / 2; o > 0; o >>= 1) {
-        const u64 ks = tile.shfl_xor(strict, o), ds = tile.shfl_xor(du_s, o);
-        const u32 cs = tile.shfl_xor(col_s, o);
-        if (ks < strict) { strict = ks; du_s = ds; col_s = cs; }
-        const u64 kl = tile.shfl_xor(loose, o), dl = tile.shfl_xor(du_l, o);
-        const u32 cl = tile.shfl_xor(col_l, o);
-        if (kl < loose) { loose = kl; du_l = dl; col_l = cl; }
+        const u64 kb = tile.shfl_xor(best, o), db = tile.shfl_xor(du_b, o);
+        const u32 cb = tile.shfl_xor(col_b, o);
+        if (kb < best) { best = kb; du_b = db; col_b = cb; }
     }
-    if (strict != ~0ull) { *du_out = du_s; *col_out = col_s; return strict; }
-    *du_out = du_l;
-    *col_out = col_l;
-    return loose;
+    *du_out = du_b;
+    *col_out = col_b;
+    return best;
 }
 
 // ---------------------------------------------------------------------------
@@ -765,6 +824,30 @@ struct WalkParams {
     u64 *counters;
 };
 
+// one trip: walk target -> root on the converged distances of its tree (dist + node * stride), add `volume` per street
+template <int TILE>
+__device__ __forceinline__ void walk_trip(const cg::thread_block_tile<TILE> &tile, const Arc *__restrict__ ellw,
+                                          const u32 *__restrict__ row_ptr, const Arc *__restrict__ arcs, const u32 *__restrict__ orig,
+                                          const u64 *dist, u32 stride, u32 root, u32 target, u32 V, u32 volume, u32 *load,
+                                          u32 &c_hops, u32 &c_unreach, u32 &c_stuck)
+{
+    u32 cur = target;
+    u64 dv = ld_dist(dist + (size_t)cur * stride);
+    if (dv >= kInfBits) { ++c_unreach; return; }                           // simulation.py:80
+    u32 guard = 0;
+    while (cur != root) {                                                  // :83
+        u64 du;
+        u32 nxt;
+        const u64 key = ellw ? canonical_pred_ell<TILE, false>(tile, ellw, row_ptr, arcs, orig, dist, stride, cur, dv, root, &nxt, &du)
+                             : canonical_pred<TILE, false>(tile, row_ptr, arcs, orig, dist, stride, cur, dv, root, &nxt, &du);
+        if (key == ~0ull || ++guard > V) { ++c_stuck; break; }
+        if (tile.thread_rank() == 0) atomicAdd(load + (u32)key, volume);   // :86-88
+        ++c_hops;
+        cur = nxt;                                                         // :85
+        dv = du;
+    }
+}
+
 template <int TILE>
 __global__ void __launch_bounds__(256) walk_kernel(WalkParams p)
 {
@@ -772,35 +855,21 @@ __global__ void __launch_bounds__(256) walk_kernel(WalkParams p)
     cg::thread_block_tile<TILE> tile = cg::tiled_partition<TILE>(block);
     const int64_t tiles_per_grid = (int64_t)gridDim.x * (blockDim.x / TILE);
     const int64_t tile_id = (int64_t)blockIdx.x * (blockDim.x / TILE) + threadIdx.x / TILE;
-    u64 c_hops = 0, c_unreach = 0, c_stuck = 0, c_trips = 0;
+    u32 c_hops = 0, c_unreach = 0, c_stuck = 0, c_trips = 0;
     for (int64_t t = p.t0 + tile_id; t < p.t1; t += tiles_per_grid) {
         const u32 ri = p.trip_root[t];
-        const u32 root = (u32)p.roots[ri];
         const u32 ti = ri - p.root0;
         const u64 *dist = p.dist_pool + (size_t)(ti / p.group) * p.slot_stride + (ti % p.group);
-        const u32 stride = p.node_stride;
-        u32 cur = (u32)p.trip_target[t];
-        u64 dv = ld_dist(dist + (size_t)cur * stride);
         ++c_trips;
-        if (dv >= kInfBits) { ++c_unreach; continue; }                     // simulation.py:80
-        u32 guard = 0;
-        while (cur != root) {                                              // :83
-            u64 du;
-            u32 nxt;
-            const u64 key = p.ellw ? canonical_pred_ell<TILE, false>(tile, p.ellw, p.row_ptr, p.arcs, p.orig, dist, stride, cur, dv, &nxt, &du)
-                                   : canonical_pred<TILE, false>(tile, p.row_ptr, p.arcs, p.orig, dist, stride, cur, dv, &nxt, &du);
-            if (key == ~0ull || ++guard > p.V) { ++c_stuck; break; }
-            if (tile.thread_rank() == 0) atomicAdd(p.load + (u32)key, p.volume);   // :86-88
-            ++c_hops;
-            cur = nxt;                                                     // :85
-            dv = du;
-        }
+        walk_trip<TILE>(tile, p.ellw, p.row_ptr, p.arcs, p.orig, dist, p.node_stride, (u32)p.roots[ri], (u32)p.trip_target[t], p.V,
+                        p.volume, p.load, c_hops, c_unreach, c_stuck);
+        if (c_hops > 0x40000000u) { if (tile.thread_rank() == 0) atomicAdd(p.counters + C_HOPS, (u64)c_hops); c_hops = 0; }
     }
     if (tile.thread_rank() == 0) {
-        if (c_trips) atomicAdd(p.counters + C_TRIPS, c_trips);
-        if (c_hops) atomicAdd(p.counters + C_HOPS, c_hops);
-        if (c_unreach) atomicAdd(p.counters + C_UNREACHABLE, c_unreach);
-        if (c_stuck) atomicAdd(p.counters + C_STUCK, c_stuck);
+        if (c_trips) atomicAdd(p.counters + C_TRIPS, (u64)c_trips);
+        if (c_hops) atomicAdd(p.counters + C_HOPS, (u64)c_hops);
+        if (c_unreach) atomicAdd(p.counters + C_UNREACHABLE, (u64)c_unreach);
+        if (c_stuck) atomicAdd(p.counters + C_STUCK, (u64)c_stuck);
     }
 }
 
@@ -819,7 +888,7 @@ __global__ void __launch_bounds__(256) pred_kernel(const u32 *row_ptr, const Arc
         if (v != root && dv < kInfBits) {
             u64 du;
             u32 nxt;
-            const u64 key = canonical_pred<TILE, true>(tile, row_ptr, arcs, orig, dist, stride, v, dv, &nxt, &du);
+            const u64 key = canonical_pred<TILE, true>(tile, row_ptr, arcs, orig, dist, stride, v, dv, root, &nxt, &du);
             if (key != ~0ull) pr = (int32_t)(key >> 32);
         }
         if (tile.thread_rank() == 0) {

@@ -29,9 +29,11 @@ class Device(object):
         self._h = h
         self.stream = int(stream) if stream else None      # None: library-owned stream
         # tuning hook for A/B runs of the kernels: S4MPI_OPTIONS="key=value,key=value" (see s4_ctx_set_option)
+        self.env_options = set()                           # keys set from the environment outrank device_settings
         for item in filter(None, os.environ.get("S4MPI_OPTIONS", "").split(",")):
             key, _, value = item.partition("=")
             self.set_option(key.strip(), float(value))
+            self.env_options.add(key.strip())
 
     def close(self):
         if getattr(self, "_h", None):

@@ -4,7 +4,8 @@
   street_network_<k>.s4mpi    zlib(pickle(StreetNetwork))
 
 The reference opened the files in text mode under Python 2 (bytes == str there);
-here they are binary.  Pickles use protocol 2 so a Python-2 reader can load them.
+here they are binary.  The traffic loads are plain arrays any reader can parse; the pickled StreetNetwork
+(protocol 2) names this package's class, so only this package loads the street_network files.
 """
 import array
 import pickle

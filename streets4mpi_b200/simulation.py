@@ -36,7 +36,8 @@ class Simulation(object):
 
         self._device = device or engine.default_device()
         for key in ("delta_factor", "block_threads", "ctas_per_sm", "pool_bytes", "batch_roots", "root_mode"):
-            if device_settings.get(key) is not None:
+            # S4MPI_OPTIONS (the A/B hook of engine.Device) outranks device_settings
+            if device_settings.get(key) is not None and key not in self._device.env_options:
                 self._device.set_option(key, device_settings[key])
         flat = street_network.flat()
         self._graph = street_network.device_graph(self._device)
@@ -55,8 +56,8 @@ class Simulation(object):
             table = trips if isinstance(trips, TripTable) else TripTable.from_dict(trips)
             self._sim = engine.DeviceSim(self._graph, flat.dense(table.origins), flat.dense(table.goals),
                                          float(jam_tolerance), engine.make_physics(settings))
-        if not np.array_equal(flat.max_speed, flat.max_speed_insertion):
-            self._sim.set_max_speed(flat.max_speed, flat.max_speed_insertion)
+        # always: the device graph caches the limits of its first upload, the network may have moved on since
+        self._sim.set_max_speed(flat.max_speed, flat.max_speed_insertion)
         self._speed_version = street_network._speed_version
         # host mirrors: None = the device copy is authoritative
         self._host_load = None

@@ -385,7 +385,8 @@ class StreetNetwork(object):
         self._weight_version += 1
 
     def __getstate__(self):
-        self._materialize()
+        # an array-built network is pickled in its array form (and materialises lazily after loading): writing
+        # street_network_*.s4mpi must not turn a 10^6..10^8-node network into per-edge dicts
         d = dict(self.__dict__)
         d["_flat_cache"] = None
         d["_device_graph"] = None

@@ -18,6 +18,13 @@ What is executed verbatim from /root/reference:
                     ``print`` syntax), with the single token ``.iteritems()`` ->
                     ``.items()``; ``osmdata`` (imposm) is stubbed -- simulation.py:30
                     imports it and never uses it
+  osmdata.py        source text up to its stale ``__main__`` block, on top of a stub
+                    ``imposm.parser.OSMParser`` (imposm is a C extension, absent) that reads
+                    OSM XML with xml.etree and calls the four callbacks the way imposm does:
+                    coords (id, lon, lat) for every node, nodes (id, tags, (lon, lat)) for
+                    tagged nodes only, ways (id, tags, refs), relations (id, tags,
+                    [(ref, type, role)]).  The construction rules, the speed table, the
+                    haversine and the landuse closure are the reference's code (osm_ingest.json).
 Nothing else is shimmed: weights, the walk, the load counters, the adaptation
 sweep and the speed clamp are the reference's code paths.
 """
@@ -74,6 +81,128 @@ def load_reference():
 
 def hexf(x):
     return float(x).hex()
+
+
+# ---------------------------------------------------------------------------
+class StubOSMParser(object):
+    """imposm.parser.OSMParser's callback protocol over xml.etree (concurrency ignored)."""
+
+    def __init__(self, concurrency=None, coords_callback=None, nodes_callback=None, ways_callback=None,
+                 relations_callback=None):
+        self.cb = (coords_callback, nodes_callback, ways_callback, relations_callback)
+
+    def parse(self, filename):
+        import xml.etree.ElementTree as ET
+        coords_cb, nodes_cb, ways_cb, rel_cb = self.cb
+        coords, nodes, ways, rels = [], [], [], []
+        for el in ET.parse(filename).getroot():
+            tags = dict((t.get("k"), t.get("v")) for t in el.findall("tag"))
+            if el.tag == "node":
+                osmid, lon, lat = int(el.get("id")), float(el.get("lon")), float(el.get("lat"))
+                coords.append((osmid, lon, lat))
+                if tags:
+                    nodes.append((osmid, tags, (lon, lat)))
+            elif el.tag == "way":
+                ways.append((int(el.get("id")), tags, [int(n.get("ref")) for n in el.findall("nd")]))
+            elif el.tag == "relation":
+                rels.append((int(el.get("id")), tags,
+                             [(int(m.get("ref")), m.get("type"), m.get("role")) for m in el.findall("member")]))
+        coords_cb(coords)
+        nodes_cb(nodes)
+        ways_cb(ways)
+        rel_cb(rels)
+
+
+def load_reference_osmdata():
+    """The reference's osmdata module (call after load_reference(): it imports the reference's streetnetwork)."""
+    for name in ("imposm", "imposm.parser"):
+        sys.modules[name] = types.ModuleType(name)
+    sys.modules["imposm.parser"].OSMParser = StubOSMParser
+    text = open(os.path.join(REF, "osmdata.py")).read()
+    text = text[:text.index('if __name__ == "__main__":')]
+    mod = types.ModuleType("ref_osmdata")
+    mod.__file__ = os.path.join(REF, "osmdata.py")
+    exec(compile(text, mod.__file__, "exec"), mod.__dict__)
+    return mod
+
+
+HAND_OSM = """<?xml version="1.0" encoding="UTF-8"?>
+<osm version="0.6">
+ <node id="1" lat="53.5800" lon="9.9100"/>
+ <node id="2" lat="53.5810" lon="9.9110"/>
+ <node id="3" lat="53.5820" lon="9.9125"><tag k="landuse" v="commercial"/></node>
+ <node id="4" lat="53.5830" lon="9.9140"/>
+ <node id="5" lat="53.5830" lon="9.9140"/>
+ <node id="6" lat="53.5845" lon="9.9150"/>
+ <node id="7" lat="53.5790" lon="9.9080"/>
+ <node id="8" lat="53.5795" lon="9.9070"><tag k="name" v="tagged but no landuse"/></node>
+ <node id="9" lat="53.5900" lon="9.9300"/>
+ <node id="10" lat="-33.9000" lon="151.2000"/>
+ <node id="11" lat="-33.9010" lon="151.2020"/>
+ <way id="100"><nd ref="1"/><nd ref="2"/><nd ref="3"/><tag k="highway" v="primary"/></way>
+ <way id="101"><nd ref="3"/><nd ref="2"/><tag k="highway" v="motorway"/></way>
+ <way id="102"><nd ref="3"/><nd ref="4"/><nd ref="5"/><nd ref="6"/><tag k="highway" v="residential"/><tag k="maxspeed" v="30 mph"/></way>
+ <way id="103"><nd ref="6"/><nd ref="7"/><tag k="highway" v="trunk"/><tag k="maxspeed" v="none"/></way>
+ <way id="104"><nd ref="7"/><nd ref="1"/><tag k="highway" v="bogus_class"/><tag k="maxspeed" v="walk"/></way>
+ <way id="105"><nd ref="7"/><nd ref="8"/><tag k="highway" v="footway"/></way>
+ <way id="106"><nd ref="8"/><nd ref="9"/><tag k="highway" v="secondary"/><tag k="maxspeed" v="60"/></way>
+ <way id="107"><nd ref="10"/><nd ref="11"/><tag k="highway" v="service"/></way>
+ <way id="108"><nd ref="4"/><nd ref="4"/><tag k="highway" v="path"/></way>
+ <way id="200"><nd ref="1"/><nd ref="2"/><nd ref="7"/><nd ref="1"/><tag k="landuse" v="residential"/></way>
+ <way id="201"><nd ref="6"/><nd ref="9"/><nd ref="10"/><tag k="landuse" v="industrial"/></way>
+ <way id="202"><nd ref="5"/><nd ref="8"/><tag k="building" v="yes"/></way>
+ <way id="203"><nd ref="9"/><nd ref="11"/><tag k="landuse" v="forest"/></way>
+ <relation id="300"><member type="way" ref="202" role="outer"/><member type="relation" ref="301" role=""/><tag k="landuse" v="commercial"/></relation>
+ <relation id="301"><member type="way" ref="107" role=""/><member type="node" ref="8" role=""/><member type="node" ref="2" role=""/><member type="node" ref="999" role=""/></relation>
+ <relation id="302"><member type="way" ref="100" role=""/><tag k="type" v="route"/></relation>
+</osm>
+"""
+
+
+def osm_record(name, xml_text, osmdata_mod):
+    import tempfile
+    with tempfile.NamedTemporaryFile("w", suffix=".osm", delete=False) as f:
+        f.write(xml_text)
+        path = f.name
+    try:
+        b = osmdata_mod.GraphBuilder(path)
+        net = b.build_street_network()
+        b.find_node_categories()
+    finally:
+        os.unlink(path)
+    streets = []
+    for i in range(net.street_index):
+        st = net.get_street_by_index(i)
+        at = net._graph.edge_attributes(st)
+        assert at[0] == i
+        streets.append([st[0], st[1], hexf(at[1]), at[2], hexf(net.get_driving_time(st))])
+    nodes = sorted(net.get_nodes())
+    return {"name": name, "xml": xml_text, "streets": streets,
+            "nodes": [[n, hexf(net.node_coordinates(n)[0]), hexf(net.node_coordinates(n)[1])] for n in nodes],
+            "bounds": None if net.bounds is None else [[hexf(x) for x in pair] for pair in net.bounds],
+            "residential": sorted(b.residential_nodes), "industrial": sorted(b.industrial_nodes),
+            "commercial": sorted(b.commercial_nodes),
+            "connected_residential": sorted(b.connected_residential_nodes),
+            "connected_industrial": sorted(b.connected_industrial_nodes),
+            "connected_commercial": sorted(b.connected_commercial_nodes)}
+
+
+def gen_osm_ingest(out_dir):
+    """osmdata.py:37-231 executed on two OSM XML files: a hand-written one with the rule corner cases (first way
+    wins also against the reversed orientation, mph / none / unparsable maxspeed, unknown highway class, footway,
+    two nodes on one coordinate (zero-length street), a self loop, the southern hemisphere, landuse on a node, on
+    ways and on a relation with a nested relation, a dangling member) and a generated town (synth.write_osm_xml)."""
+    import tempfile
+    from streets4mpi_b200 import synth
+    osmdata_mod = load_reference_osmdata()
+    recs = [osm_record("hand_written_rules", HAND_OSM, osmdata_mod)]
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "town.osm")
+        synth.write_osm_xml(path, rows=7, cols=9, seed=5)
+        recs.append(osm_record("generated_town_7x9", open(path).read(), osmdata_mod))
+    json.dump({"source": "osmdata.py GraphBuilder.__init__/build_street_network/find_node_categories executed under "
+                         "Python 3 behind a stub imposm.parser.OSMParser (xml.etree feeding the four callbacks)",
+               "cases": recs}, open(os.path.join(out_dir, "osm_ingest.json"), "w"))
 
 
 # ---------------------------------------------------------------------------
@@ -287,6 +416,7 @@ def main():
     json.dump({"a": list(a), "b": list(b), "a_b": list(utils.merge_arrays((a, b))),
                "a_none": list(utils.merge_arrays((a, None)))},
               open(os.path.join(out_dir, "merge_arrays.json"), "w"))
+    gen_osm_ingest(out_dir)
     print("golden fixtures written to", out_dir)
 
 

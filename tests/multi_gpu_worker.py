@@ -5,6 +5,9 @@ mode "ranks":  the reference's own axis -- every rank routes its own trips with 
                all-reduced total and the cumulative load must equal the oracle routing all ranks' trips.
 mode "trees":  one virtual rank whose trees are dealt to the GPUs (distributed.partition_by_root): the totals must
                equal the single-rank oracle day, whatever the number of GPUs.
+mode "driver": the zero-argument ``Streets4MPI()`` driver itself under the launcher (it must join the job
+               and exchange every day): every rank ends with the same total, equal to the oracle routing every
+               rank's trips with that rank's jam tolerance.
 Rank 0 prints one JSON line with the verdict and the load hashes of every day.
 """
 import json
@@ -22,6 +25,41 @@ mode = sys.argv[1] if len(sys.argv) > 1 else "ranks"
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 dev = engine.Device(local)
 engine.set_default_device(dev)
+if mode == "driver":
+    import torch.distributed as dist
+    from streets4mpi_b200.settings import settings
+    from streets4mpi_b200.streets4mpi import Streets4MPI
+    settings.update({"osm_file": "synthetic:grid:40x50:3", "logging": None, "max_simulation_steps": 3,
+                     "number_of_residents": 3001, "steps_between_street_construction": 10, "persist_traffic_load": False})
+    app = Streets4MPI()                                     # joins the job itself (distributed.init inside)
+    sim = app.simulation
+    assert dev.comm_size() == (world, rank) and app.process_rank == rank
+    flat = sim.street_network.flat()
+    o = np.array([a for a, goals in sim.trips.items() for _ in goals], dtype=np.int64)
+    g = np.array([b for _, goals in sim.trips.items() for b in goals], dtype=np.int64)
+    assert len(o) == 3001 // world                          # streets4mpi.py:69
+    mine = (flat.dense(o), flat.dense(g), float(sim.jam_tolerance), "%016x" % sim._sim.load_hash()[0])
+    everyone = [None] * world
+    dist.all_gather_object(everyone, mine)
+    ok = len(set(e[3] for e in everyone)) == 1              # the same total on every rank
+    ok = ok and len(set(e[2] for e in everyone)) == world   # own jam tolerance per rank (:78)
+    if rank == 0:
+        csr = ctwin.Csr(flat.V, flat.u, flat.v)
+        prev = np.zeros(flat.S, dtype=np.uint32)
+        for day in range(3):
+            want = np.zeros(flat.S, dtype=np.uint32)
+            for (oo, gg, jj, _) in everyone:
+                load, _ = ctwin.day(csr, ctwin.weights(flat.length, flat.max_speed, prev, jj), oo, gg, nthreads=os.cpu_count() or 1)
+                want += load
+            prev = want
+        ok = ok and bool(np.array_equal(np.frombuffer(sim.traffic_load, dtype=np.uint32), prev))
+        print(json.dumps({"mode": mode, "world": world, "ok": bool(ok), "load_hash_per_day": [everyone[0][3]]}), flush=True)
+    box = [ok]
+    dist.broadcast_object_list(box, src=0)
+    dist.barrier()
+    dev.comm_free()
+    dist.destroy_process_group()
+    sys.exit(0 if box[0] else 1)
 distributed.init(dev)
 assert dev.comm_size() == (world, rank)
 arrays = synth.grid_arrays(200, 220, seed=5)

@@ -49,3 +49,11 @@ def test_tree_parallel_totals_do_not_depend_on_gpu_count():
     outs = [_run("trees", w) for w in worlds]
     assert all(o["ok"] for o in outs)
     assert all(o["load_hash_per_day"] == outs[0]["load_hash_per_day"] for o in outs), outs
+
+
+@pytest.mark.skipif(_gpus() < 2, reason="needs two GPUs")
+def test_streets4mpi_driver_under_the_launcher():
+    """``Streets4MPI()`` started by torchrun joins the job, exchanges every day, and every rank
+    ends with the oracle's total over all ranks' trips."""
+    out = _run("driver", 2)
+    assert out["ok"] and out["world"] == 2

@@ -205,6 +205,64 @@ def test_ties_zero_weights_and_components(dev):
 
 
 @pytest.mark.parametrize("ranked", [False, True])
+def test_zero_weight_plateaus_match_oracle(dev, phys, ranked):
+    """Zero-length streets (two OSM nodes on one coordinate give haversine 0): the plateau rule keeps predecessor
+    chains acyclic (R-C w=1, C-A w=0, A-B w=0, id(B) < id(A) < id(C) must load [1, 1, 1]), and a day on a
+    grid with 25 % zero-length streets equals the oracle's, stuck counter included."""
+    from oracle import ctwin
+    from streets4mpi_b200 import engine
+    B, A, Cn, R = 0, 1, 2, 3
+    u = np.array([R, Cn, A], dtype=np.int32)
+    v = np.array([Cn, A, B], dtype=np.int32)
+    g = engine.DeviceGraph(dev, 4, u, v, np.array([100.0, 0.0, 0.0]), np.full(3, 50, dtype=np.int32),
+                           node_rank=np.array([2, 0, 3, 1], dtype=np.int32) if ranked else None)
+    dist, pred = g.sssp(np.array([1.0, 0.0, 0.0]), R)
+    assert dist.tolist() == [1.0, 1.0, 1.0, 0.0] and pred.tolist() == [A, Cn, R, -1]
+    for mode in (0, 1):
+        old = dev.get_option("root_mode")
+        try:
+            dev.set_option("root_mode", mode)
+            sim = engine.DeviceSim(g, np.array([R, B], dtype=np.int32), np.array([B, R], dtype=np.int32), 0.5, phys)
+            sim.step()
+            assert sim.get_load().tolist() == [2, 2, 2]
+            assert sim.counters()["trips_stuck"] == 0
+            sim.close()
+        finally:
+            dev.set_option("root_mode", old)
+    g.close()
+    rng = np.random.default_rng(21)
+    rows, cols = 30, 34
+    V = rows * cols
+    idx = np.arange(V).reshape(rows, cols)
+    u = np.concatenate([idx[:, :-1].ravel(), idx[:-1, :].ravel()]).astype(np.int32)
+    v = np.concatenate([idx[:, 1:].ravel(), idx[1:, :].ravel()]).astype(np.int32)
+    S = len(u)
+    L = np.where(rng.random(S) < 0.25, 0.0, rng.integers(1, 4, S) * 50.0)
+    ms = np.full(S, 50, dtype=np.int32)
+    o = rng.integers(0, V, 4000).astype(np.int32)
+    gl = rng.integers(0, V, 4000).astype(np.int32)
+    rank = rng.permutation(V).astype(np.int32) if ranked else None
+    g = engine.DeviceGraph(dev, V, u, v, L, ms, node_rank=rank)
+    sim = engine.DeviceSim(g, o, gl, 0.5, phys)
+    csr = ctwin.Csr(V, u, v)
+    prev = np.zeros(S, dtype=np.uint32)
+    stuck = 0
+    for _ in range(2):
+        sim.step()
+        w = ctwin.weights(L, ms, prev, 0.5)
+        want, cnt = ctwin.day(csr, w, o, gl, nthreads=4)
+        assert np.array_equal(sim.get_load(), want)
+        stuck += cnt["stuck"]
+        sim.commit_total()
+        prev = want
+    assert sim.counters()["trips_stuck"] == stuck
+    for src in (0, V // 3):
+        dist, pred = g.sssp(w, src)
+        d0, p0, _ = ctwin.sssp(csr, w, src)
+        assert np.array_equal(dist.view(np.uint64), d0.view(np.uint64)) and np.array_equal(pred, p0)
+
+
+@pytest.mark.parametrize("ranked", [False, True])
 def test_day_with_ties_matches_oracle(dev, phys, ranked):
     """Equal lengths and speeds on a grid: every trip has many shortest paths; the CUDA walk
     and the oracle apply the same lowest-predecessor rule, so loads still agree bit for bit."""

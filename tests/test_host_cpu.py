@@ -53,8 +53,8 @@ def test_product_never_imports_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
-                assert "oracle" not in text.replace("oracle/", "").replace("``oracle", "") or f == "_ffi.py" or True
                 assert "import oracle" not in text and "from oracle" not in text
+                assert "libs4oracle" not in text and "oracle/_build" not in text and "ctwin" not in text
 
 
 def test_street_network_api_matches_reference_fixture():
@@ -108,6 +108,11 @@ def test_street_network_from_arrays_equals_call_by_call():
         assert np.array_equal(getattr(fa, name), getattr(fb, name)), name
     assert sorted(a) == sorted(b)
     assert a.has_node(5) and not a.has_node(10 ** 7)
+    # pickling (street_network_*.s4mpi) keeps the array form of the live object and of the clone
+    c = synth.network_from(arr)
+    clone = pickle.loads(pickle.dumps(c, protocol=2))
+    assert c._arrays is not None and clone._arrays is not None
+    assert np.array_equal(clone.flat().length, fa.length) and sorted(clone) == sorted(b)
     assert a.get_street_index((1, 0)) == 0            # materialises the dict form
     assert a.flat().S == fb.S
 
@@ -272,6 +277,39 @@ def test_osm_ingest_rules(tmp_path):
     assert b.get_all_child_nodes(123456789) == set()
     flat = net.flat()
     assert flat.locality_rank() is not None and sorted(flat.locality_rank().tolist()) == list(range(120))
+
+
+def test_osm_ingest_matches_reference_fixture(tmp_path):
+    """f3 pinned: tests/golden/osm_ingest.json holds what the reference's own osmdata.py (executed behind a stub
+    imposm parser, tests/golden/make_golden.py) builds from two OSM XML files; this package's reader must build the
+    same street list (order, fp64 lengths and driving times bit for bit, speed limits), node coordinates, bounds
+    and landuse node sets."""
+    from streets4mpi_b200.osmdata import GraphBuilder
+    for case in load_golden("osm_ingest.json")["cases"]:
+        path = str(tmp_path / (case["name"] + ".osm"))
+        with open(path, "w") as f:
+            f.write(case["xml"])
+        b = GraphBuilder(path)
+        net = b.build_street_network()
+        b.find_node_categories()
+        assert net.street_index == len(case["streets"])
+        for i, (u, v, length, ms, w) in enumerate(case["streets"]):
+            st = net.get_street_by_index(i)
+            assert tuple(st) == (u, v), (case["name"], i)
+            at = net._graph.edge_attributes(st)
+            assert at[0] == i and float(at[1]).hex() == length and at[2] == ms
+            assert float(net.get_driving_time(st)).hex() == w
+        assert sorted(net.get_nodes()) == [n for n, _, _ in case["nodes"]]
+        for n, lon, lat in case["nodes"]:
+            assert [float(x).hex() for x in net.node_coordinates(n)] == [lon, lat]
+        assert [[float(x).hex() for x in pair] for pair in net.bounds] == case["bounds"]
+        for key in ("residential", "industrial", "commercial"):
+            assert sorted(getattr(b, key + "_nodes")) == case[key], (case["name"], key)
+            assert sorted(getattr(b, "connected_" + key + "_nodes")) == case["connected_" + key], (case["name"], key)
+        # the array view the device consumes carries the same numbers
+        flat = net.flat()
+        assert [float(x).hex() for x in flat.length] == [s[2] for s in case["streets"]]
+        assert flat.max_speed.tolist() == [s[3] for s in case["streets"]]
 
 
 def test_visualization_modes_without_gpu(tmp_path):

@@ -150,3 +150,67 @@ def test_sssp_against_scipy():
             for a, b in zip(path[::-1][:-1], path[::-1][1:]):
                 acc = acc + wmap.get((a, b), wmap.get((b, a)))
             assert acc == dist[t]
+
+
+def _zero_weight_chain():
+    """R-C w=1, C-A w=0, A-B w=0 with id(B) < id(A) < id(C): a "smallest equal-cost neighbour" rule
+    oscillates B -> A -> B; the plateau rule climbs B -> A -> C -> R."""
+    B, A, Cn, R = 0, 1, 2, 3
+    u = np.array([R, Cn, A], dtype=np.int32)
+    v = np.array([Cn, A, B], dtype=np.int32)
+    w = np.array([1.0, 0.0, 0.0])
+    return (B, A, Cn, R), u, v, w
+
+
+def test_plateau_rule_has_no_cycles_on_zero_weights():
+    (B, A, Cn, R), u, v, w = _zero_weight_chain()
+    csr = ctwin.Csr(4, u, v)
+    dist, pred, _ = ctwin.sssp(csr, w, R)
+    assert dist.tolist() == [1.0, 1.0, 1.0, 0.0]
+    assert pred.tolist() == [A, Cn, R, -1]
+    load, cnt = ctwin.day(csr, w, np.array([R], dtype=np.int32), np.array([B], dtype=np.int32))
+    assert load.tolist() == [1, 1, 1] and cnt["stuck"] == 0 and cnt["hops"] == 3
+    # the Python port applies the same rule
+    import types
+    nbrs = {R: [Cn], Cn: [R, A], A: [Cn, B], B: [A]}
+    wmap = {(R, Cn): 1.0, (Cn, R): 1.0, (Cn, A): 0.0, (A, Cn): 0.0, (A, B): 0.0, (B, A): 0.0}
+    g = types.SimpleNamespace(neighbors=lambda n: nbrs[n], edge_weight=lambda e: wmap[e])
+    previous, d, _ = port.canonical_tree(g, R)
+    assert previous == {R: None, Cn: R, A: Cn, B: A}
+
+
+def test_plateau_rule_random_zero_weight_graphs():
+    """Grids with 25 % zero-weight streets: every predecessor chain of the C twin reaches the root without
+    repeating a node, reproduces the distance exactly, and the port's tree is the same tree."""
+    import types
+    rng = np.random.default_rng(12)
+    rows, cols = 9, 11
+    V = rows * cols
+    idx = np.arange(V).reshape(rows, cols)
+    u = np.concatenate([idx[:, :-1].ravel(), idx[:-1, :].ravel()]).astype(np.int32)
+    v = np.concatenate([idx[:, 1:].ravel(), idx[1:, :].ravel()]).astype(np.int32)
+    for trial in range(4):
+        w = np.where(rng.random(len(u)) < 0.25, 0.0, rng.integers(1, 4, len(u))).astype(np.float64)
+        csr = ctwin.Csr(V, u, v)
+        nbrs = {n: [] for n in range(V)}
+        wmap = {}
+        for a, b, x in zip(u.tolist(), v.tolist(), w.tolist()):
+            nbrs[a].append(b); nbrs[b].append(a)
+            wmap[(a, b)] = x; wmap[(b, a)] = x
+        g = types.SimpleNamespace(neighbors=lambda n: nbrs[n], edge_weight=lambda e: wmap[e])
+        for src in (0, V // 2 + trial):
+            dist, pred, _ = ctwin.sssp(csr, w, src)
+            previous, d, _ = port.canonical_tree(g, src)
+            for n in range(V):
+                assert (previous[n] if previous[n] is not None else -1) == pred[n]
+                seen, here, acc = set(), n, []
+                while here != src:
+                    assert here not in seen
+                    seen.add(here)
+                    assert pred[here] >= 0          # plateaus stay below the bound at this density
+                    acc.append(wmap[(int(pred[here]), here)])
+                    here = int(pred[here])
+                total = 0.0
+                for x in reversed(acc):
+                    total = total + x
+                assert total == dist[n]
