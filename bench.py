@@ -439,16 +439,23 @@ def gpu_arm(args):
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    day_marks = []
     barrier()
     with torch.cuda.stream(stream):
         e0.record(stream)
         for _ in range(args.steps):
             day_resident()
+            if args.per_day:                                # one more event per day: where the days of a long run differ
+                day_marks.append(torch.cuda.Event(enable_timing=True))
+                day_marks[-1].record(stream)
         e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
+    per_day_ms = [a.elapsed_time(b) for a, b in zip([e0] + day_marks[:-1], day_marks)]
     clocks = sampler.stop() if rank == 0 else None
     c = sim.counters()
+    adapt_events = sum(1 for d in range(args.warmup, args.warmup + args.steps)
+                       if args.construction_every and d > 0 and d % args.construction_every == 0)
     # the state after warm-up + K days: uint32 sums are exact, so in strong mode these do not depend on N
     load_hash, cum_hash = sim._sim.load_hash()
     t_ms = torch.tensor([ms], dtype=torch.float64, device="cuda:%d" % local)
@@ -641,6 +648,10 @@ def gpu_arm(args):
                     "api": "reference driver protocol (streets4mpi.py:93-100): Simulation.step(), array('I') "
                            "traffic_load read + assign, merge_arrays into cumulative_traffic_load; wall clock"},
             "gpu_launches": int(launches),
+            "per_day_ms_rank0": [round(x, 3) for x in per_day_ms] if args.per_day else None,
+            "road_construction": {"events_in_timed_region": adapt_events,
+                                  "ms_per_event_rank0": c["ms_adapt"] / adapt_events if adapt_events else None,
+                                  "note": "K5: CUB radix sort of (cumulative load, street) + adapt_kernel, simulation.py:91-109"},
             "clocks": clocks,
             "setup_seconds": setup_s,
         }
@@ -674,6 +685,7 @@ def main():
     ap.add_argument("--north-star", action="store_true", help="measure the 10 M-trip day at any GPU count (default: at 8)")
     ap.add_argument("--extra-graphs", default="road1m,planar1m", help="workloads measured as secondary days at N=1")
     ap.add_argument("--faithful-trees-per-core", type=int, default=1)
+    ap.add_argument("--per-day", action="store_true", help="record the device time of every timed day (rank 0)")
     args = ap.parse_args()
     global TRIPS_OVERRIDE
     TRIPS_OVERRIDE = args.trips

@@ -221,6 +221,10 @@ int s4_sim_get_max_speed(s4_sim *sim, int32_t *visible_out, int32_t *insertion_o
 int s4_sim_set_max_speed(s4_sim *sim, const int32_t *visible, const int32_t *insertion_or_null);
 
 int s4_sim_get_counters(s4_sim *sim, s4_counters *out);
+/* Trips whose walk found no predecessor since the last reset (simulation.py:83-85 would raise KeyError there): only
+ * possible on a zero-weight plateau of more than 32 nodes.  Cheap (8 bytes D2H behind the stream); the host layer
+ * warns when the number grows. */
+int s4_sim_trips_stuck(s4_sim *sim, uint64_t *out);
 int s4_sim_reset_counters(s4_sim *sim);
 
 /* calculate_driving_speed (simulation.py:129-138) for n streets, on the device */

@@ -87,6 +87,7 @@ SIGNATURES = {
     "s4_sim_set_max_speed": (C.c_int, [_vp, _i32p, _i32p]),
     "s4_sim_get_counters": (C.c_int, [_vp, C.POINTER(Counters)]),
     "s4_sim_reset_counters": (C.c_int, [_vp]),
+    "s4_sim_trips_stuck": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "s4_driving_speed": (C.c_int, [_vp, C.c_int64, _f64p, _i32p, _u32p, C.POINTER(Physics), _f64p]),
 }
 

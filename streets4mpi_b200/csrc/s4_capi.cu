@@ -75,6 +75,8 @@ struct Options {
     double lag_factor = 1.0;        // source-batched kernel: hold a node back by this multiple of the root-to-root distance
     int group_log = 0;              // diagnostics: keep per-group cycles / rounds / entries of the last day (s4_graph_group_log)
     int min_batches = 4;            // a day is cut into at least this many (SSSP launch -> walk) batches when lanes = 2
+    int cluster = 0;                // CTAs of a thread-block cluster that share one group of trees (1 | 2 | 4 | 8); 0 = from
+                                    // the number of slots that fit in the pool (large graphs: fewer slots than SMs)
 };
 
 // how the trees of a launch are laid out in the distance pool
@@ -173,6 +175,7 @@ struct s4_graph {
     bool ws_auto = false;      // workspace sized by the library (not by the "queue_entries" option)
     u32 near_gcap = 0, far_cap = 0;
     DevBuf<u32> work_counters;
+    DevBuf<u32> cluster_ctl;   // control words of the clusters (cluster > 1), two lanes
     DevBuf<u32> glog;          // diagnostics of the source-batched kernel: 4 words per group of the last day
     int64_t glog_groups = 0;
     // single-source API scratch
@@ -209,13 +212,16 @@ struct s4_sim {
     std::vector<int64_t> h_root_off;   // Dp+1
     int64_t alg_arcs_per_day = 0, alg_nodes_per_day = 0;
     DevBuf<u32> load, cum;
+    DevBuf<uint2> deferred;        // T: trips the hot walk kernel hands to the slow one (zero-weight plateaus)
+    DevBuf<u32> deferred_counts;   // one per batch of the day
     bool has_cum = false;
     DevBuf<int32_t> ms_vis, ms_ins;
     DevBuf<double> w_street;
     DevBuf<Arc> arcs;              // CSR records (walk, overflow arcs)
     DevBuf<Arc> ell;               // fixed-stride records (SSSP)
     DevBuf<Arc> ellw;              // fixed-stride records with street indices (walk); empty when walk_ell = 0
-    DevBuf<double> wsum;
+    DevBuf<double> wsum;           // bucket-width scale of the day: (median street weight) * S
+    DevBuf<u32> w_hist;            // histogram of the day's weights (weights_street_kernel -> weight_scale_kernel)
     DevBuf<u64> counters;
     bool weights_valid = false;
     // sort scratch for K5
@@ -321,6 +327,7 @@ static void option_slot(Options &o, const char *key, int *kind, void **raw)
         {"walk_ell", 1, &o.walk_ell},                {"group_lanes", 1, &o.group_lanes},
         {"group_words", 1, &o.group_words},         {"lag_factor", 0, &o.lag_factor},
         {"min_batches", 1, &o.min_batches},         {"group_log", 1, &o.group_log},
+        {"cluster", 1, &o.cluster},
     };
     for (auto &it : items)
         if (strcmp(it.k, key) == 0) { *kind = it.kind; *raw = it.p; return; }
@@ -349,7 +356,8 @@ extern "C" int s4_ctx_set_option(s4_ctx *ctx, const char *key, double value)
               (t.preread == 1 || t.preread == 2) && (t.lanes == 1 || t.lanes == 2) &&
               t.early_advance >= 0 && t.early_advance <= 64 && (t.walk_ell == 0 || t.walk_ell == 1) &&
               (t.group_lanes == 0 || t.group_lanes == 4 || t.group_lanes == 8) && (t.group_words == 1 || t.group_words == 2) &&
-              t.lag_factor >= 0.0 && t.lag_factor <= 64.0 && t.min_batches >= 1 && t.min_batches <= 64;
+              t.lag_factor >= 0.0 && t.lag_factor <= 64.0 && t.min_batches >= 1 && t.min_batches <= 64 &&
+              (t.cluster == 0 || t.cluster == 1 || t.cluster == 2 || t.cluster == 4 || t.cluster == 8);
     if (!ok) return fail(S4_ERR_ARG, "option '%s': value %g out of range", key, value);
     ctx->opt = trial;
     return S4_OK;
@@ -792,8 +800,15 @@ static GroupKernel pick_group_block(int block)
     return nullptr;
 }
 
-static GroupKernel pick_group(int block, int lanes, int words)
+static GroupKernel pick_group(int block, int lanes, int words, int cl)
 {
+    if (cl > 1) {
+        // clusters: the wide-row layout on wide CTAs only (the case they exist for: huge graphs, few slots)
+        if (lanes != 8 || words != 2) return nullptr;
+        if (block == 1024) return cl == 2 ? sssp_group_kernel<1024, 8, 2, 2> : cl == 4 ? sssp_group_kernel<1024, 8, 2, 4> : sssp_group_kernel<1024, 8, 2, 8>;
+        if (block == 512) return cl == 2 ? sssp_group_kernel<512, 8, 2, 2> : cl == 4 ? sssp_group_kernel<512, 8, 2, 4> : sssp_group_kernel<512, 8, 2, 8>;
+        return nullptr;
+    }
     if (lanes == 8 && words == 1) return pick_group_block<8, 1>(block);
     if (lanes == 8 && words == 2) return pick_group_block<8, 2>(block);
     if (lanes == 4 && words == 1) return pick_group_block<4, 1>(block);
@@ -806,8 +821,10 @@ struct SsspLaunch {
     GroupKernel gfn = nullptr;      // ... or a group of trees per CTA
     Layout lay;
     int block = 0, grid = 0;
+    int cl = 1;                     // CTAs per group (thread-block cluster size)
     size_t smem = 0;
     u32 scap = 0;
+    int units() const { return grid / cl; }     // frontier workspaces a launch needs: one per CTA, or per cluster
     const void *func() const { return gfn ? (const void *)gfn : (const void *)fn; }
 };
 
@@ -842,22 +859,31 @@ static int plan_sssp(s4_graph *g, SsspLaunch *L)
     // relaxation round; the source-batched kernel spends group_lanes lanes on every node it expands
     int block = o.block_threads ? o.block_threads : grouped ? std::min(1024, g->auto_block * o.group_lanes / 2) : g->auto_block;
     block = std::max(block, 32);
-    if (!o.block_threads) {
-        // narrow CTAs only pay off when that many slots fit in flight
+    const int sms = g->ctx->prop.multiProcessorCount;
+    int cl = 1;
+    {
         double pool_budget = 0.0, ws_budget = 0.0;
         int rc = scratch_budget(g, &pool_budget, &ws_budget);
         if (rc) return rc;
         const double per_slot = 8.0 * (double)slot_words(g, L->lay);
         const int64_t slots = o.batch_roots > 0 ? std::max<int64_t>(1, o.batch_roots / L->lay.K) : (int64_t)(pool_budget / per_slot);
-        const int64_t per_lane = std::max<int64_t>(1, slots / 2);
-        while (block < 1024 && (int64_t)g->ctx->prop.multiProcessorCount * std::min(32, 1024 / block) > per_lane) block *= 2;
+        const int64_t per_lane = std::max<int64_t>(1, slots / (o.lanes >= 2 ? 2 : 1));
+        // narrow CTAs only pay off when that many slots fit in flight
+        if (!o.block_threads)
+            while (block < 1024 && (int64_t)sms * std::min(32, 1024 / block) > per_lane) block *= 2;
+        // fewer slots than SMs (10^7 .. 10^8 nodes): the CTAs of a cluster share a group
+        if (grouped && o.group_lanes == 8 && o.group_words == 2 && block >= 512) {
+            if (o.cluster > 0) cl = o.cluster;
+            else while (cl < 8 && per_lane * (cl * 2) * (1024 / block) <= (int64_t)sms) cl *= 2;
+        }
     }
-    const int near_entries = o.near_smem_entries ? o.near_smem_entries : grouped ? std::max(256, 8 * block) : std::max(128, 6 * block);
+    const int near_entries = cl > 1 ? 0 : o.near_smem_entries ? o.near_smem_entries : grouped ? std::max(256, 8 * block) : std::max(128, 6 * block);
     const int ctas = o.ctas_per_sm ? o.ctas_per_sm : std::min(32, std::max(1, 1024 / block));
+    L->cl = cl;
     if (grouped) {
-        L->gfn = pick_group(block, o.group_lanes, o.group_words);
+        L->gfn = pick_group(block, o.group_lanes, o.group_words, cl);
         L->fn = nullptr;
-        if (!L->gfn) return fail(S4_ERR_ARG, "no source-batched SSSP kernel for block=%d lanes=%d words=%d", block, o.group_lanes, o.group_words);
+        if (!L->gfn) return fail(S4_ERR_ARG, "no source-batched SSSP kernel for block=%d lanes=%d words=%d cluster=%d", block, o.group_lanes, o.group_words, cl);
     } else {
         L->fn = pick_sssp(block);
         L->gfn = nullptr;
@@ -870,7 +896,23 @@ static int plan_sssp(s4_graph *g, SsspLaunch *L)
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, L->func(), L->block, L->smem));
     if (occ < 1) return fail(S4_ERR_ARG, "SSSP kernel does not fit on an SM (block=%d, smem=%zu)", L->block, L->smem);
-    L->grid = g->ctx->prop.multiProcessorCount * std::min(occ, ctas);
+    L->grid = sms * std::min(occ, ctas);
+    if (cl > 1) {
+        // co-scheduled clusters the device can hold (GPC boundaries cost a few SMs)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(sms / cl * cl));
+        cfg.blockDim = dim3((unsigned)L->block);
+        cfg.dynamicSmemBytes = L->smem;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        int n_clusters = 0;
+        CU(cudaOccupancyMaxActiveClusters(&n_clusters, L->func(), &cfg));
+        if (n_clusters < 1) return fail(S4_ERR_ARG, "no cluster of %d CTAs of %d threads fits on this device", cl, L->block);
+        L->grid = n_clusters * cl;
+    }
     return S4_OK;
 }
 
@@ -890,23 +932,29 @@ static int ensure_scratch(s4_graph *g, const SsspLaunch &L, int64_t slots_wanted
     g->pool_slots = (int64_t)(g->pool.n / sw);
     // per-CTA spill / far-pile capacity: a quarter of the nodes for a 256-wide CTA, proportionally less for
     // the narrow CTAs used on thin-wave graphs (an overflow is survivable: Bellman-Ford safety net)
+    // The source-batched kernel queues a node at most once per round (stamps), so V entries can never overflow its near
+    // queues: it gets that much when the budget below allows.
     int64_t q = o.queue_entries > 0 ? o.queue_entries
-                                    : std::max<int64_t>(8192, std::max<int64_t>(65536, V / 4) * std::min(L.block, 256) / 256);
+                : L.gfn         ? std::max<int64_t>(8192, V)
+                                : std::max<int64_t>(8192, std::max<int64_t>(65536, V / 4) * std::min(L.block, 256) / 256);
     q = std::min<int64_t>(q, std::max<int64_t>(V, 1024) * 2);
     if (o.queue_entries <= 0) {
         // many narrow CTAs on a large graph: keep the whole workspace (two lanes x CTAs x four queues x 12 B) inside
         // its share of the device memory; a wave is far thinner than V / 4 on road graphs
-        const double per_entry = 2.0 * (double)L.grid * 4.0 * (double)(sizeof(u32) + sizeof(u64));
+        const double per_entry = 2.0 * (double)L.units() * 4.0 * (double)(sizeof(u32) + sizeof(u64));
         q = std::max<int64_t>(8192, std::min<int64_t>(q, (int64_t)(ws_budget / per_entry)));
     }
     // an automatically sized workspace is kept while it is large enough (its budget moves with the free memory)
     const bool explicit_q = o.queue_entries > 0;
-    if (L.grid > g->ws_ctas || !g->ws_v.p || (explicit_q ? (u32)q != g->near_gcap : !g->ws_auto)) {
+    if (L.cl > 1) {
+        CU(g->cluster_ctl.ensure((size_t)2 * L.units() * GC_WORDS));
+    }
+    if (L.units() > g->ws_ctas || !g->ws_v.p || (explicit_q ? (u32)q != g->near_gcap : !g->ws_auto)) {
         g->ws_v.release();
         g->ws_d.release();
-        CU(g->ws_v.alloc((size_t)2 * L.grid * 4 * (size_t)q));      // two lanes (concurrent launches)
-        CU(g->ws_d.alloc((size_t)2 * L.grid * 4 * (size_t)q));
-        g->ws_ctas = L.grid;
+        CU(g->ws_v.alloc((size_t)2 * L.units() * 4 * (size_t)q));   // two lanes (concurrent launches)
+        CU(g->ws_d.alloc((size_t)2 * L.units() * 4 * (size_t)q));
+        g->ws_ctas = L.units();
         g->near_gcap = (u32)q;
         g->far_cap = (u32)q;
         g->ws_auto = !explicit_q;
@@ -944,9 +992,25 @@ static int launch_sssp(s4_graph *g, const SsspLaunch &L, const Arc *rows, const 
         p.near_gcap = g->near_gcap;
         p.far_cap = g->far_cap;
         p.adaptive = (u32)o.adaptive_delta;
-        p.early_advance = (u32)(o.early_advance * (L.block / o.group_lanes) / 8);
+        p.early_advance = (u32)(o.early_advance * (L.block / o.group_lanes) * L.cl / 8);
         p.counters = counters;
         p.group_log = o.group_log && g->glog.p ? g->glog.p + (size_t)first_group_of_day * 4 : nullptr;
+        p.cluster_ctl = nullptr;
+        if (L.cl > 1) {
+            p.cluster_ctl = g->cluster_ctl.p + (size_t)lane * L.units() * GC_WORDS;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(std::min(L.units(), std::max(1, p.n_groups)) * L.cl));
+            cfg.blockDim = dim3((unsigned)L.block);
+            cfg.dynamicSmemBytes = L.smem;
+            cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = (unsigned)L.cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            CU(cudaLaunchKernelEx(&cfg, L.gfn, p));
+            return S4_OK;
+        }
         const int grid = std::min(L.grid, std::max(1, p.n_groups));
         L.gfn<<<grid, L.block, L.smem, st>>>(p);
         CU(cudaGetLastError());
@@ -1000,11 +1064,13 @@ static int launch_walk(s4_graph *g, const WalkParams &p, cudaStream_t st)
     const int tile = g->ctx->opt.walk_tile ? g->ctx->opt.walk_tile : g->auto_walk_tile;
     const int block = 256;
     const int grid = grid_for((p.t1 - p.t0) * tile, block, g->ctx);
+    // behind it: the trips it stopped on a zero-weight plateau (none on positive weights: the kernel exits at once)
+    const int slow_grid = g->ctx->prop.multiProcessorCount;
     switch (tile) {
-        case 4: walk_kernel<4><<<grid, block, 0, st>>>(p); break;
-        case 8: walk_kernel<8><<<grid, block, 0, st>>>(p); break;
-        case 16: walk_kernel<16><<<grid, block, 0, st>>>(p); break;
-        default: walk_kernel<32><<<grid, block, 0, st>>>(p); break;
+        case 4: walk_kernel<4><<<grid, block, 0, st>>>(p); walk_slow_kernel<4><<<slow_grid, block, 0, st>>>(p); break;
+        case 8: walk_kernel<8><<<grid, block, 0, st>>>(p); walk_slow_kernel<8><<<slow_grid, block, 0, st>>>(p); break;
+        case 16: walk_kernel<16><<<grid, block, 0, st>>>(p); walk_slow_kernel<16><<<slow_grid, block, 0, st>>>(p); break;
+        default: walk_kernel<32><<<grid, block, 0, st>>>(p); walk_slow_kernel<32><<<slow_grid, block, 0, st>>>(p); break;
     }
     CU(cudaGetLastError());
     return S4_OK;
@@ -1034,8 +1100,18 @@ extern "C" int s4_graph_sssp(s4_graph *g, const double *w_street, int32_t origin
     CU(g->wsum_tmp.ensure(1));
     CU(g->work_counters.ensure(1024));
     cudaStream_t st = ctx->stream;
+    // bucket-width scale like the simulation's: (median positive weight) * S
     double wsum = 0.0;
-    for (int64_t s = 0; s < g->S; ++s) wsum += w_street[s];
+    {
+        std::vector<double> pos;
+        pos.reserve((size_t)g->S);
+        for (int64_t s = 0; s < g->S; ++s)
+            if (w_street[s] > 0.0 && !std::isinf(w_street[s])) pos.push_back(w_street[s]);
+        if (!pos.empty()) {
+            std::nth_element(pos.begin(), pos.begin() + (pos.size() - 1) / 2, pos.end());
+            wsum = pos[(pos.size() - 1) / 2] * (double)g->S;
+        }
+    }
     if (g->S > 0) CU(cudaMemcpyAsync(g->w_tmp.p, w_street, (size_t)g->S * sizeof(double), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(g->wsum_tmp.p, &wsum, sizeof(double), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(g->root_tmp.p, &origin_dev, sizeof(int32_t), cudaMemcpyHostToDevice, st));
@@ -1473,12 +1549,19 @@ static int run_weights(s4_sim *sim, int reset_load)
     s4_graph *g = sim->g;
     s4_ctx *ctx = g->ctx;
     cudaStream_t st = ctx->stream;
-    CU(cudaMemsetAsync(sim->wsum.p, 0, sizeof(double), st));
+    if (!sim->w_hist.p) {
+        CU(sim->w_hist.alloc(kWeightBins));
+        CU(cudaMemsetAsync(sim->w_hist.p, 0, kWeightBins * sizeof(u32), st));     // weight_scale_kernel clears it after use
+    }
     if (g->S > 0) {
         weights_street_kernel<<<grid_for(g->S, 256, ctx), 256, 0, st>>>(g->S, g->length.p, sim->ms_vis.p, sim->load.p, sim->jam,
-                                                                        sim->ph, reset_load, sim->w_street.p, sim->wsum.p);
+                                                                        sim->ph, reset_load, sim->w_street.p, sim->w_hist.p);
         CU(cudaGetLastError());
-        ++sim->acc.kernel_launches;
+        weight_scale_kernel<<<1, 1024, 0, st>>>(sim->w_hist.p, g->S, sim->wsum.p);   // bucket-width scale: median weight * S
+        CU(cudaGetLastError());
+        sim->acc.kernel_launches += 2;
+    } else {
+        CU(cudaMemsetAsync(sim->wsum.p, 0, sizeof(double), st));
     }
     if (g->A > 0) {
         weights_arc_kernel<<<grid_for(g->A, 256, ctx), 256, 0, st>>>(g->A, g->arc_cs.p, sim->w_street.p, sim->arcs.p);
@@ -1563,6 +1646,9 @@ extern "C" int s4_sim_step(s4_sim *sim)
     if (n_batches > 0) {
         CU(g->work_counters.ensure((size_t)std::max<int64_t>(n_batches, 1024)));
         CU(cudaMemsetAsync(g->work_counters.p, 0, g->work_counters.n * sizeof(u32), st));
+        CU(sim->deferred.ensure((size_t)std::max<int64_t>(sim->T, 1)));
+        CU(sim->deferred_counts.ensure((size_t)std::max<int64_t>(n_batches, 1024)));
+        CU(cudaMemsetAsync(sim->deferred_counts.p, 0, sim->deferred_counts.n * sizeof(u32), st));
     }
     if (split) {                                                   // lane 1 starts after K1 and the counter reset
         CU(cudaEventRecord(ctx->sssp_done[0], st));
@@ -1599,10 +1685,13 @@ extern "C" int s4_sim_step(s4_sim *sim)
         wp.volume = sim->volume;
         wp.load = sim->load.p;
         wp.counters = sim->counters.p;
+        wp.t_base = wp.t0;
+        wp.deferred = sim->deferred.p + wp.t0;
+        wp.deferred_count = sim->deferred_counts.p + bi;
         if ((rc = ev_begin(sim->ev_walk, sim->used_walk, ls))) return rc;
         if ((rc = launch_walk(g, wp, ls))) return rc;
         if ((rc = ev_end(sim->ev_walk, sim->used_walk, ls))) return rc;
-        ++sim->acc.kernel_launches;
+        sim->acc.kernel_launches += 2;
     }
     if (split) {                                                   // the day ends when both lanes are done
         CU(cudaEventRecord(ctx->walk_done[1], ctx->walk_stream));
@@ -1856,6 +1945,18 @@ extern "C" int s4_sim_get_counters(s4_sim *sim, s4_counters *out)
     out->trips_unreachable = h[C_UNREACHABLE];
     out->trips_stuck = h[C_STUCK];
     out->hops = h[C_HOPS];
+    return S4_OK;
+}
+
+extern "C" int s4_sim_trips_stuck(s4_sim *sim, uint64_t *out)
+{
+    CHECK_ARG(sim && out, "s4_sim_trips_stuck: NULL argument");
+    s4_ctx *ctx = sim->g->ctx;
+    CU(cudaSetDevice(ctx->device));
+    u64 v = 0;
+    CU(cudaMemcpyAsync(&v, sim->counters.p + C_STUCK, sizeof v, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    *out = v;
     return S4_OK;
 }
 

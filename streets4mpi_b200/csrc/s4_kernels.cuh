@@ -91,29 +91,61 @@ __device__ __forceinline__ double driving_time(double length, double max_speed, 
     return __ddiv_rn(length, perceived);                                       // :63
 }
 
-// per street: weight of the day from yesterday's total load; optionally reset
-// the load counter (simulation.py:68) and accumulate sum(w) for the bucket width.
-__global__ void weights_street_kernel(int64_t S, const double *__restrict__ length,
-                                      const int32_t *__restrict__ max_speed, u32 *__restrict__ load,
-                                      double jam, Phys ph, int reset_load, double *__restrict__ w_street,
-                                      double *__restrict__ wsum)
+// per street: weight of the day from yesterday's total load; optionally reset the load counter (simulation.py:68) and
+// build the histogram the bucket width is derived from.
+// Bucket width (a heuristic: no result depends on it).  delta is a multiple of the TYPICAL street weight.  The mean is
+// a poor "typical" once road construction has pushed unused streets down to 1 km/h (weights 30-50x the bulk: the mean
+// follows them, buckets hold most of the graph, frontiers overflow); the median does not move.  The weights are
+// binned by the top 14 bits of their fp64 pattern (exponent + 2 mantissa bits: bin edges 19 % apart, 8192 bins for
+// positive finite values), privatised per block in shared memory; weight_scale_kernel then reads off the median bin.
+static constexpr int kWeightBins = 8192;
+
+__global__ void __launch_bounds__(256) weights_street_kernel(int64_t S, const double *__restrict__ length,
+                                                             const int32_t *__restrict__ max_speed, u32 *__restrict__ load,
+                                                             double jam, Phys ph, int reset_load, double *__restrict__ w_street,
+                                                             u32 *__restrict__ hist)
 {
-    double local = 0.0;
+    __shared__ u32 h[kWeightBins];
+    for (int i = threadIdx.x; i < kWeightBins; i += blockDim.x) h[i] = 0u;
+    __syncthreads();
     for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < S; s += (int64_t)gridDim.x * blockDim.x) {
         double w = driving_time(length[s], (double)max_speed[s], (double)load[s], jam, ph);
         w_street[s] = w;
         if (reset_load) load[s] = 0u;
-        local += w;
+        const u32 hi = hi32((u64)__double_as_longlong(w));
+        if (w > 0.0 && hi < 0x7FF00000u) atomicAdd(&h[hi >> 18], 1u);
     }
-    // block reduction of the (heuristic-only) weight sum
-    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
-    __shared__ double part[32];
-    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = local;
     __syncthreads();
-    if (threadIdx.x < 32) {
-        double v = threadIdx.x < (blockDim.x + 31) / 32 ? part[threadIdx.x] : 0.0;
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (threadIdx.x == 0) atomicAdd(wsum, v);
+    for (int i = threadIdx.x; i < kWeightBins; i += blockDim.x)
+        if (h[i]) atomicAdd(hist + i, h[i]);
+}
+
+// one block: the median bin of the histogram -> scale[0] = (typical weight) * S, the quantity the SSSP kernels
+// multiply by delta_factor / S; clears the histogram for the next day
+__global__ void __launch_bounds__(1024) weight_scale_kernel(u32 *__restrict__ hist, int64_t S, double *__restrict__ scale)
+{
+    constexpr int PER = kWeightBins / 1024;
+    __shared__ unsigned long long part[1024];
+    u32 mine[PER];
+    unsigned long long sum = 0;
+    for (int k = 0; k < PER; ++k) { mine[k] = hist[threadIdx.x * PER + k]; hist[threadIdx.x * PER + k] = 0u; sum += mine[k]; }
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {                       // inclusive scan
+        const unsigned long long v = threadIdx.x >= (u32)o ? part[threadIdx.x - o] : 0ull;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    const unsigned long long total = part[1023], half = (total + 1) / 2;
+    if (total == 0) { if (threadIdx.x == 0) scale[0] = 0.0; return; }
+    unsigned long long before = part[threadIdx.x] - sum;
+    if (before < half && part[threadIdx.x] >= half) {          // exactly one thread
+        int k = 0;
+        while (before + mine[k] < half) before += mine[k++];
+        const u32 bin = threadIdx.x * PER + k;
+        // centre of the bin: lower edge * 2^(1/8)
+        scale[0] = __hiloint2double((int)(bin << 18), 0) * 1.0905077326652577 * (double)S;
     }
 }
 
@@ -640,9 +672,14 @@ __device__ __noinline__ u64 next_candidate(const u32 *__restrict__ row_ptr, cons
     return best;
 }
 
-// every lane of the tile runs the same search on the same data (uniform, the loads broadcast)
-__device__ __noinline__ u64 plateau_first_hop(const u32 *__restrict__ row_ptr, const Arc *__restrict__ arcs, const u32 *__restrict__ orig,
-                                              const u64 *dist, u32 stride, u32 v, u32 root, u32 *col_out)
+// every lane of the tile runs the same search on the same data (uniform, the loads broadcast).  The result comes
+// back by value: an out-pointer into the caller's frame would force the walk's loop variables into local memory.
+struct PlateauHop {
+    u64 key;    // (id(u) << 32 | street) of the first hop, ~0: none (plateau larger than the bound)
+    u32 col;    // its device number
+};
+__device__ __noinline__ PlateauHop plateau_first_hop(const u32 *__restrict__ row_ptr, const Arc *__restrict__ arcs, const u32 *__restrict__ orig,
+                                                     const u64 *dist, u32 stride, u32 v, u32 root)
 {
     u32 seen[kPlateauMax], first_col[kPlateauMax];
     u64 first_key[kPlateauMax];
@@ -661,23 +698,24 @@ __device__ __noinline__ u64 plateau_first_hop(const u32 *__restrict__ row_ptr, c
             bool dup = false;
             for (int k = 0; k < n_seen; ++k) dup = dup || seen[k] == cu;
             if (dup) continue;
-            if (n_seen >= kPlateauMax) { *col_out = 0u; return ~0ull; }
+            if (n_seen >= kPlateauMax) return PlateauHop{~0ull, 0u};
             seen[n_seen] = cu;
             first_key[n_seen] = head == 0 ? key : first_key[head];
             first_col[n_seen] = head == 0 ? cu : first_col[head];
             u32 dummy;
-            if (cu == root || next_candidate(row_ptr, arcs, orig, dist, stride, cu, false, 0ull, true, &dummy) != ~0ull) {
-                *col_out = first_col[n_seen];
-                return first_key[n_seen];
-            }
+            if (cu == root || next_candidate(row_ptr, arcs, orig, dist, stride, cu, false, 0ull, true, &dummy) != ~0ull)
+                return PlateauHop{first_key[n_seen], first_col[n_seen]};
             ++n_seen;
         }
     }
-    *col_out = 0u;
-    return ~0ull;
+    return PlateauHop{~0ull, 0u};
 }
 
-template <int TILE, bool WANT_ID>
+// DEFER_PLATEAU: do not search, return kPlateauKey (the hot walk kernel hands such trips to walk_slow_kernel: a call
+// to the search would raise the register count of the whole kernel to the callee's).
+static constexpr u64 kPlateauKey = ~1ull;
+
+template <int TILE, bool WANT_ID, bool DEFER_PLATEAU = false>
 __device__ __forceinline__ u64 canonical_pred(const cg::thread_block_tile<TILE> &tile, const u32 *__restrict__ row_ptr,
                                               const Arc *__restrict__ arcs, const u32 *__restrict__ orig, const u64 *dist,
                                               u32 stride, u32 cur, u64 dv, u32 root, u32 *col_out, u64 *du_out)
@@ -715,8 +753,11 @@ __device__ __forceinline__ u64 canonical_pred(const cg::thread_block_tile<TILE> 
     if ((total & 0xFFFFu) == 0u) { *du_out = 0; *col_out = 0; return ~0ull; }
     if (closer == 0u) {
         // plateau: every candidate is at dist[cur]
+        if constexpr (DEFER_PLATEAU) { *du_out = dv; *col_out = cur; return kPlateauKey; }
+        const PlateauHop h = plateau_first_hop(row_ptr, arcs, orig, dist, stride, cur, root);
         *du_out = dv;
-        return plateau_first_hop(row_ptr, arcs, orig, dist, stride, cur, root, col_out);
+        *col_out = h.col;
+        return h.key;
     }
     // several closer candidates: smallest (id, street)
     u64 best = ~0ull, du_b = 0;
@@ -747,23 +788,25 @@ __device__ __forceinline__ u64 canonical_pred(const cg::thread_block_tile<TILE> 
 // The same rule on the fixed-stride rows (ellw: first kEllWidth arcs of every node, lane k of the tile looks at slot
 // k): one dependent memory stage less per hop than the CSR (no row_ptr lookup).  Nodes with more arcs fall back to
 // canonical_pred.  Padding slots point back at `cur` and are skipped like self loops.
-template <int TILE, bool WANT_ID>
+template <int TILE, bool WANT_ID, bool DEFER_PLATEAU = false>
 __device__ __forceinline__ u64 canonical_pred_ell(const cg::thread_block_tile<TILE> &tile, const Arc *__restrict__ ellw,
                                                   const u32 *__restrict__ row_ptr, const Arc *__restrict__ arcs,
                                                   const u32 *__restrict__ orig, const u64 *dist, u32 stride, u32 cur, u64 dv,
-                                                  u32 root, u32 *col_out, u64 *du_out)
+                                                  u32 root, u32 *col_out, u64 *du_out, u32 skip = ~0u)
 {
+    // skip: a neighbour known to be strictly farther from the root than `cur` (the node a walk just came from through a
+    // closer-candidate hop): it cannot reproduce dist[cur], its distance is not read (one DRAM sector less per hop)
     static_assert(TILE >= kEllWidth, "one lane per slot");
     const u32 lane = tile.thread_rank();
     Arc a;
     a.col = cur; a.street = 0u; a.w = 0.0;
     if (lane < (u32)kEllWidth) a = ld_arc(ellw + (size_t)cur * kEllWidth + lane);
     if (tile.any(lane == 0u && (a.col & kOvfBit) != 0u))
-        return canonical_pred<TILE, WANT_ID>(tile, row_ptr, arcs, orig, dist, stride, cur, dv, root, col_out, du_out);
+        return canonical_pred<TILE, WANT_ID, DEFER_PLATEAU>(tile, row_ptr, arcs, orig, dist, stride, cur, dv, root, col_out, du_out);
     const u32 col = a.col;
     u64 du = 0;
     bool match = false;
-    if (lane < (u32)kEllWidth && col != cur) {
+    if (lane < (u32)kEllWidth && col != cur && col != skip) {
         du = ld_dist(dist + (size_t)col * stride);
         const u64 ndb = (u64)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)du), a.w));
         match = du < kInfBits && ndb == dv;
@@ -781,8 +824,11 @@ __device__ __forceinline__ u64 canonical_pred_ell(const cg::thread_block_tile<TI
     }
     if (mc == 0u) {
         if (!tile.any(match)) { *du_out = 0; *col_out = 0; return ~0ull; }
-        *du_out = dv;                                                    // plateau
-        return plateau_first_hop(row_ptr, arcs, orig, dist, stride, cur, root, col_out);
+        if constexpr (DEFER_PLATEAU) { *du_out = dv; *col_out = cur; return kPlateauKey; }
+        const PlateauHop h = plateau_first_hop(row_ptr, arcs, orig, dist, stride, cur, root);   // plateau
+        *du_out = dv;
+        *col_out = h.col;
+        return h.key;
     }
     // several closer candidates: smallest (id, street)
     u64 best = ~0ull, du_b = 0;
@@ -822,30 +868,36 @@ struct WalkParams {
     u32 volume;
     u32 *load;
     u64 *counters;
+    uint2 *deferred;            // {trip - t_base, node}: trips stopped on a zero-weight plateau (walk_slow_kernel)
+    u32 *deferred_count;        // zeroed before the walk of a batch
+    int64_t t_base;             // first trip of this batch (deferred entries are relative to it)
 };
 
-// one trip: walk target -> root on the converged distances of its tree (dist + node * stride), add `volume` per street
-template <int TILE>
-__device__ __forceinline__ void walk_trip(const cg::thread_block_tile<TILE> &tile, const Arc *__restrict__ ellw,
-                                          const u32 *__restrict__ row_ptr, const Arc *__restrict__ arcs, const u32 *__restrict__ orig,
-                                          const u64 *dist, u32 stride, u32 root, u32 target, u32 V, u32 volume, u32 *load,
-                                          u32 &c_hops, u32 &c_unreach, u32 &c_stuck)
+// one trip: walk from `cur` (distance dv) to the root on the converged distances of its tree (dist + node * stride), add
+// `volume` per street.  DEFER: on a zero-weight plateau stop and return the node (the caller queues the trip for
+// walk_slow_kernel); otherwise search the plateau in place.  Returns ~0u when the trip is finished.
+template <int TILE, bool DEFER>
+__device__ __forceinline__ u32 walk_trip(const cg::thread_block_tile<TILE> &tile, const Arc *__restrict__ ellw,
+                                         const u32 *__restrict__ row_ptr, const Arc *__restrict__ arcs, const u32 *__restrict__ orig,
+                                         const u64 *dist, u32 stride, u32 root, u32 cur, u64 dv, u32 V, u32 volume, u32 *load,
+                                         u32 &c_hops, u32 &c_stuck)
 {
-    u32 cur = target;
-    u64 dv = ld_dist(dist + (size_t)cur * stride);
-    if (dv >= kInfBits) { ++c_unreach; return; }                           // simulation.py:80
     u32 guard = 0;
-    while (cur != root) {                                                  // :83
+    u32 prev = ~0u;                  // DEFER: every hop so far went to a strictly closer node, so `prev` is strictly farther
+    while (cur != root) {                                                  // simulation.py:83
         u64 du;
         u32 nxt;
-        const u64 key = ellw ? canonical_pred_ell<TILE, false>(tile, ellw, row_ptr, arcs, orig, dist, stride, cur, dv, root, &nxt, &du)
-                             : canonical_pred<TILE, false>(tile, row_ptr, arcs, orig, dist, stride, cur, dv, root, &nxt, &du);
+        const u64 key = ellw ? canonical_pred_ell<TILE, false, DEFER>(tile, ellw, row_ptr, arcs, orig, dist, stride, cur, dv, root, &nxt, &du, prev)
+                             : canonical_pred<TILE, false, DEFER>(tile, row_ptr, arcs, orig, dist, stride, cur, dv, root, &nxt, &du);
+        if (DEFER && key == kPlateauKey) return cur;
         if (key == ~0ull || ++guard > V) { ++c_stuck; break; }
         if (tile.thread_rank() == 0) atomicAdd(load + (u32)key, volume);   // :86-88
         ++c_hops;
+        if (DEFER) prev = cur;
         cur = nxt;                                                         // :85
         dv = du;
     }
+    return ~0u;
 }
 
 template <int TILE>
@@ -860,15 +912,49 @@ __global__ void __launch_bounds__(256) walk_kernel(WalkParams p)
         const u32 ri = p.trip_root[t];
         const u32 ti = ri - p.root0;
         const u64 *dist = p.dist_pool + (size_t)(ti / p.group) * p.slot_stride + (ti % p.group);
+        const u32 target = (u32)p.trip_target[t];
         ++c_trips;
-        walk_trip<TILE>(tile, p.ellw, p.row_ptr, p.arcs, p.orig, dist, p.node_stride, (u32)p.roots[ri], (u32)p.trip_target[t], p.V,
-                        p.volume, p.load, c_hops, c_unreach, c_stuck);
+        const u64 dv = ld_dist(dist + (size_t)target * p.node_stride);
+        if (dv >= kInfBits) { ++c_unreach; continue; }                     // simulation.py:80
+        const u32 at = walk_trip<TILE, true>(tile, p.ellw, p.row_ptr, p.arcs, p.orig, dist, p.node_stride, (u32)p.roots[ri], target, dv,
+                                             p.V, p.volume, p.load, c_hops, c_stuck);
+        if (at != ~0u && tile.thread_rank() == 0) {
+            // a zero-weight plateau: the rest of this trip is walked by walk_slow_kernel
+            const u32 slot = atomicAdd(p.deferred_count, 1u);
+            p.deferred[slot] = make_uint2((u32)(t - p.t_base), at);
+        }
         if (c_hops > 0x40000000u) { if (tile.thread_rank() == 0) atomicAdd(p.counters + C_HOPS, (u64)c_hops); c_hops = 0; }
     }
     if (tile.thread_rank() == 0) {
         if (c_trips) atomicAdd(p.counters + C_TRIPS, (u64)c_trips);
         if (c_hops) atomicAdd(p.counters + C_HOPS, (u64)c_hops);
         if (c_unreach) atomicAdd(p.counters + C_UNREACHABLE, (u64)c_unreach);
+        if (c_stuck) atomicAdd(p.counters + C_STUCK, (u64)c_stuck);
+    }
+}
+
+// The trips walk_kernel stopped on a zero-weight plateau, continued with the full rule (bounded plateau search).  Rare
+// (zero-length streets); launched behind every walk_kernel on the same stream, a no-op when the list is empty.
+template <int TILE>
+__global__ void __launch_bounds__(256) walk_slow_kernel(WalkParams p)
+{
+    cg::thread_block block = cg::this_thread_block();
+    cg::thread_block_tile<TILE> tile = cg::tiled_partition<TILE>(block);
+    const u32 tiles_per_grid = gridDim.x * (blockDim.x / TILE);
+    const u32 n = *p.deferred_count;
+    u32 c_hops = 0, c_stuck = 0;
+    for (u32 i = blockIdx.x * (blockDim.x / TILE) + threadIdx.x / TILE; i < n; i += tiles_per_grid) {
+        const uint2 d = p.deferred[i];
+        const int64_t t = p.t_base + (int64_t)d.x;
+        const u32 ri = p.trip_root[t];
+        const u32 ti = ri - p.root0;
+        const u64 *dist = p.dist_pool + (size_t)(ti / p.group) * p.slot_stride + (ti % p.group);
+        const u64 dv = ld_dist(dist + (size_t)d.y * p.node_stride);
+        walk_trip<TILE, false>(tile, p.ellw, p.row_ptr, p.arcs, p.orig, dist, p.node_stride, (u32)p.roots[ri], d.y, dv, p.V, p.volume,
+                               p.load, c_hops, c_stuck);
+    }
+    if (tile.thread_rank() == 0) {
+        if (c_hops) atomicAdd(p.counters + C_HOPS, (u64)c_hops);
         if (c_stuck) atomicAdd(p.counters + C_STUCK, (u64)c_stuck);
     }
 }

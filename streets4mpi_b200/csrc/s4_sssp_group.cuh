@@ -23,6 +23,13 @@
 // Lag.  With lag_factor > 0 the key of v is min_k dist_k[v] + L, L = lag_factor * (largest finite distance between
 // two roots of the group so far): v is expanded once the slowest tree's wave has had time to arrive too.
 // No result depends on it.
+//
+// Clusters (CL > 1).  A slot is V * RW * 8 bytes: on graphs with 10^7 .. 10^8 nodes only a few dozen fit in HBM, fewer
+// than there are SMs.  Then the CL CTAs of a thread-block cluster share ONE group: its frontier queues and far piles
+// live in the cluster's global workspace, the queue counters in a small control block in global memory, every round
+// ends with a cluster barrier instead of __syncthreads, and the entries of a round / the far pile / the slot fill
+// are dealt out to the CTAs in strides.  CL = 1 is the plain one-CTA-per-group kernel (shared-memory counters and
+// queue heads; the code paths below are selected at compile time).
 #pragma once
 
 #include "s4_kernels.cuh"
@@ -52,7 +59,11 @@ struct GroupParams {
     u32 early_advance;      // admit the next bucket when a round (not the first two of its bucket) has fewer entries
     u64 *counters;
     u32 *group_log;         // diagnostics (may be null): per group {SM cycles >> 10, rounds, entries popped, bucket advances}
+    u32 *cluster_ctl;       // CL > 1: 16 control words per cluster (queue counters, overflow flag, current group)
 };
+
+// control words of a cluster (CL > 1)
+enum GroupCtl { GC_CNT = 0, GC_FAR_CNT = 3, GC_FAR_MIN = 5, GC_OVERFLOW = 7, GC_GROUP = 8, GC_CHANGED = 9, GC_WORDS = 16 };
 
 template <int TL>
 __device__ __forceinline__ void ld_words(const u64 *p, u64 (&x)[TL])
@@ -165,7 +176,7 @@ __device__ __forceinline__ u32 subwarp_min4(u32 x0, u32 x1, u32 x2, u32 x3, u32 
     return z;
 }
 
-template <int BLOCK, int LP, int TL>
+template <int BLOCK, int LP, int TL, int CL = 1>
 __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024 / BLOCK : 1)) sssp_group_kernel(GroupParams p)
 {
     static_assert(BLOCK % 32 == 0, "whole warps");
@@ -200,8 +211,19 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024
     const bool meta_lane = t == (u32)LP - 1u;
     const u32 V = p.V;
     const size_t ws_stride = (size_t)2 * gcap + (size_t)2 * fcap;
-    u32 *wv = p.ws_v + (size_t)blockIdx.x * ws_stride;
-    u32 *wk = p.ws_k + (size_t)blockIdx.x * ws_stride;
+    // cluster: rank of this CTA, the cluster's workspace and control words; the accessors pick shared or global state
+    const u32 crank = CL > 1 ? blockIdx.x % (u32)CL : 0u;
+    const u32 unit = CL > 1 ? blockIdx.x / (u32)CL : blockIdx.x;
+    u32 *const ctl = CL > 1 ? p.cluster_ctl + (size_t)unit * GC_WORDS : nullptr;
+    const bool lead = tid == 0 && crank == 0u;                    // the one thread that owns the shared control state
+    auto CNT = [&](u32 i) -> u32 * { if constexpr (CL > 1) return ctl + GC_CNT + i; else return &s_cnt[i]; };
+    auto FAR_CNT = [&](u32 i) -> u32 * { if constexpr (CL > 1) return ctl + GC_FAR_CNT + i; else return &s_far_cnt[i]; };
+    auto FAR_MIN = [&](u32 i) -> u32 * { if constexpr (CL > 1) return ctl + GC_FAR_MIN + i; else return &s_far_min[i]; };
+    auto OVERFLOW = [&]() -> u32 * { if constexpr (CL > 1) return ctl + GC_OVERFLOW; else return &s_overflow; };
+    auto rd = [&](const u32 *q) -> u32 { if constexpr (CL > 1) return __ldcg(q); else return *q; };
+    auto sync_all = [&]() { if constexpr (CL > 1) cg::this_cluster().sync(); else __syncthreads(); };
+    u32 *wv = p.ws_v + (size_t)unit * ws_stride;
+    u32 *wk = p.ws_k + (size_t)unit * ws_stride;
     auto target = [&](u32 nb, u32 nf_) {
         return GroupPushTarget{sv0 + nb * scap, wv, wk, nb * gcap - scap, 2u * gcap + nf_ * fcap, scap, scap + gcap, fcap};
     };
@@ -211,10 +233,11 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024
     if (tid == 0) { s_stat[0] = 0u; s_stat[1] = 0u; s_stat[2] = 0u; }
 
     for (;;) {
-        __syncthreads();                       // previous group fully retired before s_* are reused
-        if (tid == 0) s_group = (int)atomicAdd(p.work_counter, 1u);
-        __syncthreads();
-        const int gi = s_group;
+        sync_all();                            // previous group fully retired before the control state is reused
+        if constexpr (CL > 1) { if (lead) ctl[GC_GROUP] = atomicAdd(p.work_counter, 1u); }
+        else if (tid == 0) s_group = (int)atomicAdd(p.work_counter, 1u);
+        sync_all();
+        const int gi = CL > 1 ? (int)__ldcg(ctl + GC_GROUP) : s_group;
         if (gi >= p.n_groups) break;
         u64 *rows = p.pool + (size_t)gi * p.slot_stride;
         int k_live = 0;                                         // trees of this group: the slots holding a root
@@ -228,28 +251,33 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024
             ulonglong2 *d2 = reinterpret_cast<ulonglong2 *>(rows);
             const size_t n2 = p.slot_stride >> 1;
             const ulonglong2 inf2 = make_ulonglong2(kInfBits, kInfBits), tail2 = make_ulonglong2(kInfBits, 0ull);
-            for (size_t i = tid; i < n2; i += BLOCK) __stcs(d2 + i, (i % (RW / 2)) == (size_t)(RW / 2 - 1) ? tail2 : inf2);
+            for (size_t i = tid + (size_t)crank * BLOCK; i < n2; i += (size_t)BLOCK * CL)
+                __stcs(d2 + i, (i % (RW / 2)) == (size_t)(RW / 2 - 1) ? tail2 : inf2);
         }
-        if (tid == 0) {
-            s_cnt[0] = (u32)k_live; s_cnt[1] = 0u; s_cnt[2] = 0u;
-            s_far_cnt[0] = 0u; s_far_cnt[1] = 0u;
-            s_far_min[0] = 0xFFFFFFFFu; s_far_min[1] = 0xFFFFFFFFu;
-            s_overflow = 0u;
+        if (lead) {
+            *CNT(0) = (u32)k_live; *CNT(1) = 0u; *CNT(2) = 0u;
+            *FAR_CNT(0) = 0u; *FAR_CNT(1) = 0u;
+            *FAR_MIN(0) = 0xFFFFFFFFu; *FAR_MIN(1) = 0xFFFFFFFFu;
+            *OVERFLOW() = 0u;
+        }
+        if (tid == 0) {                                         // replicated per CTA: every CTA of a cluster computes the same
             s_bucket_rounds = 0u; s_bucket_entries = 0u;
             s_lag_hi = 0u;
             s_glog[0] = 0u; s_glog[1] = 0u; s_glog[2] = 0u;
             s_t0 = clock64();
             s_dmul = 1.0; s_lag = 0.0; s_lag_scale = 1.0;
         }
-        __syncthreads();
+        sync_all();
         if (tid < (u32)k_live) {                                // after the fill: the roots, queued for round 1
             const u32 r = (u32)p.roots[gi * K + (int)tid];
             s_roots[tid] = r;
-            rows[(size_t)r * RW + tid] = 0ull;
-            reinterpret_cast<u32 *>(rows + (size_t)r * RW + K)[0] = 1u;
-            sv0[tid] = r;
+            if (crank == 0u) {
+                rows[(size_t)r * RW + tid] = 0ull;
+                reinterpret_cast<u32 *>(rows + (size_t)r * RW + K)[0] = 1u;
+                if constexpr (CL > 1) wv[tid] = r; else sv0[tid] = r;
+            }
         }
-        __syncthreads();
+        sync_all();
 
         u32 c = 0;          // index of the current near counter
         u32 b = 0;          // current near buffer
@@ -264,15 +292,15 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024
         u32 rib = 0;                // rounds in the current bucket
         bool force_round = false;   // an early advance found the far pile empty: run the round instead
         for (;;) {
-            const u32 n = s_cnt[c];
+            const u32 n = rd(CNT(c));
             const bool early = n > 0u && n < p.early_advance && rib >= 2u && !force_round;
             if (n > 0 && !early) {
                 ++rib;
                 force_round = false;
                 // ------------------------- relaxation round -------------------------
                 const u32 cn = c == 2 ? 0 : c + 1;
+                if (lead) *CNT(cn == 2 ? 0 : cn + 1) = 0u;             // counter of the round after next
                 if (tid == 0) {
-                    s_cnt[cn == 2 ? 0 : cn + 1] = 0u;                  // counter of the round after next
                     s_bucket_rounds += 1u;
                     s_bucket_entries += n;
                     s_stat[1] += 1u;
@@ -286,8 +314,8 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024
                 const u32 rid_next = rid + 1u;
                 const double thr_up = __hiloint2double((int)(thr_hi + 1u), 0);   // upper end of the bucket
                 const double lag = s_lag;
-                for (u32 base = 0; base < n_s; base += PW) {
-                    const u32 i = base + sub;
+                for (u32 base = 0; base < n_s; base += PW * (u32)CL) {
+                    const u32 i = base + crank * PW + sub;
                     const bool valid = i < n_s;                             // uniform in the sub-warp
                     u32 u = 0;
                     Arc a[kEllWidth];
@@ -297,7 +325,8 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024
 #pragma unroll
                     for (int j = 0; j < kEllWidth; ++j) { a[j].col = 0u; a[j].street = 0u; a[j].w = 0.0; }
                     if (valid) {
-                        u = i < scap ? csv[i] : wv[cur_off + i];
+                        if constexpr (CL > 1) u = __ldcg(wv + cur_off + i);          // written by any CTA of the cluster
+                        else u = i < scap ? csv[i] : wv[cur_off + i];
                         const Arc *row = p.ellw + (size_t)u * kEllWidth;
                         ld_row_half(row, a[0], a[1]);
                         ld_row_half(row + 2, a[2], a[3]);
@@ -354,7 +383,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024
                             } else ++c_dup;
                         } else kind = 2u;
                     }
-                    warp_push_g(kind, pv, key, lane, tg, &s_cnt[cn], &s_far_cnt[f], &s_far_min[f], &s_overflow, c_push);
+                    warp_push_g(kind, pv, key, lane, tg, CNT(cn), FAR_CNT(f), FAR_MIN(f), OVERFLOW(), c_push);
                     if (valid && t == 0u) ++c_pop;
                     // nodes with more than kEllWidth arcs: the rest of the CSR row, one arc per step
                     if (__any_sync(0xffffffffu, ovf)) {
@@ -390,12 +419,12 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024
                                     } else ++c_dup;
                                 } else k1 = 2u;
                             }
-                            warp_push_g(k1, v1, key1, lane, tg, &s_cnt[cn], &s_far_cnt[f], &s_far_min[f], &s_overflow, c_push);
+                            warp_push_g(k1, v1, key1, lane, tg, CNT(cn), FAR_CNT(f), FAR_MIN(f), OVERFLOW(), c_push);
                             if (act) ++e;
                         }
                     }
                 }
-                __syncthreads();
+                sync_all();
                 c = cn;
                 b ^= 1u;
                 rid = rid_next;
@@ -404,15 +433,15 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024
             // ------------------------- near queue empty (or thin): advance the bucket -------------------------
             // every thread must have read s_cnt[c] before the split starts refilling that queue; past this barrier no
             // push is in flight, so the far pile's counters are stable
-            __syncthreads();
-            const u32 nf_raw = s_far_cnt[f];
+            sync_all();
+            const u32 nf_raw = rd(FAR_CNT(f));
             if (nf_raw == 0u) {
                 if (n == 0u) break;                                     // group complete
                 force_round = true;                                     // nothing to admit yet
                 continue;
             }
             const u32 nf = nf_raw < fcap ? nf_raw : fcap;
-            const u32 far_min_hi = s_far_min[f];
+            const u32 far_min_hi = rd(FAR_MIN(f));
             rib = 0;
             if (tid == 0) { s_stat[0] += 1u; s_glog[2] += 1u; }
             // lag: the largest finite distance between two roots of the group (values only decrease towards the
@@ -435,8 +464,8 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024
                 if (p.adaptive) {
                     const u32 br = s_bucket_rounds, be = s_bucket_entries;
                     if (br > 0u) {
-                        if (be < br * (PW / 2u) && dmul < 16.0) dmul *= 1.5;
-                        else if (be > br * (PW * 4u) && dmul > 1.0) dmul *= (1.0 / 1.5);
+                        if (be < br * (PW * (u32)CL / 2u) && dmul < 16.0) dmul *= 1.5;
+                        else if (be > br * (PW * (u32)CL * 4u) && dmul > 1.0) dmul *= (1.0 / 1.5);
                     }
                 }
                 double delta = p.delta_scale * __ldg(p.wsum);
@@ -448,12 +477,12 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024
             const u32 fo = f ^ 1u;
             const u32 src_off = 2u * gcap + f * fcap;
             const GroupPushTarget tg = target(b, fo);
-            for (u32 base = 0; base < nf; base += BLOCK) {
-                const u32 i = base + tid;
+            for (u32 base = 0; base < nf; base += BLOCK * (u32)CL) {
+                const u32 i = base + crank * BLOCK + tid;
                 u32 k1 = 0u, v1 = 0u, key1 = 0u;
                 if (i < nf) {
-                    v1 = __ldcs(wv + src_off + i);
-                    key1 = __ldcs(wk + src_off + i);
+                    if constexpr (CL > 1) { v1 = __ldcg(wv + src_off + i); key1 = __ldcg(wk + src_off + i); }
+                    else { v1 = __ldcs(wv + src_off + i); key1 = __ldcs(wk + src_off + i); }
                     if (key1 <= thr_hi) {
                         // admitted: unless the node is already queued for the coming round
                         const u32 old = atomicExch(reinterpret_cast<u32 *>(rows + (size_t)v1 * RW + K), rid);
@@ -461,29 +490,31 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024
                     } else k1 = 2u;
                 }
                 // the round after this reads (b, c); kept entries go to the other pile (never more than nf)
-                warp_push_g(k1, v1, key1, lane, tg, &s_cnt[c], &s_far_cnt[fo], &s_far_min[fo], &s_overflow, c_push);
+                warp_push_g(k1, v1, key1, lane, tg, CNT(c), FAR_CNT(fo), FAR_MIN(fo), OVERFLOW(), c_push);
             }
-            __syncthreads();
-            if (tid == 0) { s_far_cnt[f] = 0u; s_far_min[f] = 0xFFFFFFFFu; s_bucket_rounds = 0u; s_bucket_entries = 0u; }
+            sync_all();
+            if (lead) { *FAR_CNT(f) = 0u; *FAR_MIN(f) = 0xFFFFFFFFu; }
+            if (tid == 0) { s_bucket_rounds = 0u; s_bucket_entries = 0u; }
             f = fo;
         }
 
         c_relax += (u64)c_pop * (u64)(kEllWidth * k_live);
         c_pop_all += c_pop;
         c_pop = 0u;     // arcs x trees of the expansions (nodes with more arcs not counted)
-        if (p.group_log && tid == 0) {
+        if (p.group_log && lead) {
             u32 *gl = p.group_log + (size_t)gi * 4;
             gl[0] = (u32)((clock64() - s_t0) >> 10); gl[1] = s_glog[0]; gl[2] = s_glog[1]; gl[3] = s_glog[2];
         }
         // ---- safety net: a queue overflowed and entries were dropped.  Sweep all nodes Bellman-Ford style
         // until nothing changes (same fixed point).
-        if (s_overflow) {
+        if (rd(OVERFLOW())) {
             for (;;) {
-                __syncthreads();
+                sync_all();
+                if constexpr (CL > 1) { if (lead) ctl[GC_CHANGED] = 0u; }
                 if (tid == 0) { s_changed = 0u; s_stat[2] += 1u; }
-                __syncthreads();
+                sync_all();
                 bool any = false;
-                for (u32 u = tid; u < V; u += BLOCK) {
+                for (u32 u = tid + crank * BLOCK; u < V; u += BLOCK * (u32)CL) {
                     const u32 rb = __ldg(p.row_ptr + u), re = __ldg(p.row_ptr + u + 1);
                     for (int k = 0; k < k_live; ++k) {
                         const u64 du = __ldcg(rows + (size_t)u * RW + k);
@@ -498,16 +529,17 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024
                         }
                     }
                 }
-                if (any) s_changed = 1u;
-                __syncthreads();
-                if (!s_changed) break;
+                if constexpr (CL > 1) { if (any) ctl[GC_CHANGED] = 1u; }
+                else if (any) s_changed = 1u;
+                sync_all();
+                if (!(CL > 1 ? __ldcg(ctl + GC_CHANGED) : s_changed)) break;
             }
         }
     }
 
     // ---- flush per-thread counters: one atomic per warp per counter
     __syncthreads();
-    u64 vals[7] = {c_relax, c_pop_all, c_dup, c_push, tid == 0 ? s_stat[0] : 0u, tid == 0 ? s_stat[1] : 0u, tid == 0 ? s_stat[2] : 0u};
+    u64 vals[7] = {c_relax, c_pop_all, c_dup, c_push, lead ? s_stat[0] : 0u, lead ? s_stat[1] : 0u, lead ? s_stat[2] : 0u};
     const int ids[7] = {C_ARCS_RELAXED, C_NODES_POPPED, C_STALE_POPS, C_PUSHES, C_ADVANCES, C_ROUNDS, C_FALLBACK_SWEEPS};
 #pragma unroll
     for (int jx = 0; jx < 7; ++jx) {

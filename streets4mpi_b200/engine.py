@@ -320,6 +320,11 @@ class DeviceSim(object):
         check(self.lib.s4_sim_set_max_speed(self._h, ptr(vis, C.c_int32),
                                             None if ins is None else ptr(ins, C.c_int32)))
 
+    def trips_stuck(self):
+        n = C.c_uint64()
+        check(self.lib.s4_sim_trips_stuck(self._h, C.byref(n)))
+        return int(n.value)
+
     def counters(self):
         c = Counters()
         check(self.lib.s4_sim_get_counters(self._h, C.byref(c)))

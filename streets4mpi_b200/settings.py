@@ -37,6 +37,9 @@ device_settings = {
     # host: same distribution (one uniform origin, one uniform goal per resident), a different but reproducible
     # list -- trip lists are run inputs -- and no Python loop over the residents.  For 10^7..10^8-trip runs.
     "sample_trips_on_device": False,
+    # Warn (RuntimeWarning + log line) when trips could not be walked back to their root: only possible on a
+    # zero-weight plateau of more than 32 nodes; the reference would have raised KeyError (simulation.py:85).
+    "warn_stuck": True,
     # SSSP kernel tunables (None = library default), see include/s4mpi.h s4_ctx_set_option
     "delta_factor": None,
     "block_threads": None,

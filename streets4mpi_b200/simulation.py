@@ -62,6 +62,7 @@ class Simulation(object):
         # host mirrors: None = the device copy is authoritative
         self._host_load = None
         self._host_load_dirty = False
+        self._stuck_seen = 0
         self._host_cum = None            # only meaningful while _cum_on_host
         self._cum_on_host = False
         self._cum_dirty = False
@@ -71,6 +72,7 @@ class Simulation(object):
     def traffic_load(self):
         if self._host_load is None:
             self._host_load = _to_array_I(self._sim.get_load())
+            self._check_stuck()
         return self._host_load
 
     @traffic_load.setter
@@ -109,9 +111,25 @@ class Simulation(object):
             self._speed_version = net._speed_version
 
     # ---------------------------------------------------------------- the day
+    def _check_stuck(self):
+        """A walk that finds no predecessor (zero-weight plateau beyond the search bound) would have raised KeyError
+        in the reference (simulation.py:85); here it is counted, and surfaced as soon as the host looks."""
+        if not device_settings.get("warn_stuck", True):
+            return
+        n = self._sim.trips_stuck()
+        self._stuck_seen = min(self._stuck_seen, n)          # the counters may have been reset meanwhile
+        if n > self._stuck_seen:
+            import warnings
+            msg = "%d trips could not be walked back to their root (zero-weight plateau); their load is partial" % (n - self._stuck_seen)
+            self._stuck_seen = n
+            self.log_callback(msg)
+            warnings.warn(msg, RuntimeWarning, stacklevel=3)
+
     def step(self):
         self.step_counter += 1
         self.log_callback("Preparing edges...")
+        if self.step_counter > 1:
+            self._check_stuck()                  # yesterday's walks (the library waits for that day here anyway)
         self._push_host_state()
         self._sim.step()                         # K1 -> K2 -> K3, asynchronous
         self._host_load = None

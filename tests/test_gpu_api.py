@@ -291,3 +291,27 @@ def _check_trips_sampled_on_the_device(dev, phys):
     s2.step()
     assert int(np.frombuffer(s2.traffic_load, dtype=np.uint32).astype(np.int64).sum()) == s2.counters()["hops"]
 
+
+
+def test_stuck_trips_are_surfaced():
+    """a walk that cannot find its way off a zero-weight plateau (more than 32 nodes here) is counted,
+    the oracle counts the same trip, and the Simulation warns as soon as the host looks at the load."""
+    from oracle import ctwin
+    from streets4mpi_b200 import Simulation, StreetNetwork
+    n = 41                                                # node 0 = root side, 1..40 a chain of zero-length streets
+    net = StreetNetwork()
+    for i in range(n + 1):
+        net.add_node(i, float(i), 0.0)
+    net.add_street((0, 1), 100.0, 50)
+    for i in range(1, n):
+        net.add_street((i, i + 1), 0.0, 50)
+    sim = Simulation(net, {0: [n, 5]}, 0.5, lambda *a: None)
+    sim.step()
+    with pytest.warns(RuntimeWarning, match="could not be walked back"):
+        load = np.frombuffer(sim.traffic_load, dtype=np.uint32)
+    flat = net.flat()
+    csr = ctwin.Csr(flat.V, flat.u, flat.v)
+    w = ctwin.weights(flat.length, flat.max_speed, np.zeros(flat.S, dtype=np.uint32), 0.5)
+    want, cnt = ctwin.day(csr, w, flat.dense([0, 0]), flat.dense([n, 5]))
+    assert cnt["stuck"] == 1 and sim.counters()["trips_stuck"] == 1
+    assert np.array_equal(load, want) and load[0] == 1     # the trip to node 5 is 4 plateau nodes from its exit

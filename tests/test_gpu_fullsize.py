@@ -120,3 +120,53 @@ def test_road_like_graph_at_scale():
         dev.set_option("root_mode", old)
     g.close()
 
+
+
+def test_cfg4_road_graph_at_5m_nodes():
+    """BASELINE.json configs[3] size: the 5 M-node road-like graph with a speed hierarchy (synth.road_arrays, mean degree
+    2.6, dead ends and cut-off junctions).  Two whole trees bit-equal to the oracle's (distances and canonical
+    predecessors), then a day of 5 k trips from 32 origins bit-equal to the oracle's load, followed by the road
+    adaptation and a second day on the changed limits."""
+    from oracle import ctwin
+    from streets4mpi_b200 import engine, synth
+    from streets4mpi_b200.settings import settings
+    dev = engine.default_device()
+    phys = engine.make_physics(settings)
+    arr = synth.road_arrays(5_000_000, seed=1)
+    flat = synth.network_from(arr).flat()
+    assert flat.V >= 5_000_000
+    g = engine.DeviceGraph(dev, flat.V, flat.u, flat.v, flat.length, flat.max_speed, node_rank=flat.locality_rank())
+    csr = ctwin.Csr(flat.V, flat.u, flat.v)
+    rng = np.random.default_rng(5)
+    w = ctwin.weights(flat.length, flat.max_speed, rng.integers(0, 400, flat.S).astype(np.uint32), 0.4)
+    for src in (flat.V // 2 + 1234, 17):
+        dist, pred = g.sssp(w, src)
+        d0, p0, tied = ctwin.sssp(csr, w, src)
+        assert np.array_equal(dist.view(np.uint64), d0.view(np.uint64))
+        assert np.array_equal(pred, p0)
+    cats = synth.node_categories(arr["node_ids"], seed=1, goal_fraction=0.02, residential_fraction=32.5 / flat.V)
+    o, gl = synth.trip_arrays(5000, cats["residential"], cats["goals"], seed=9)
+    od, gd = flat.dense(o), flat.dense(gl)
+    old = dev.get_option("root_mode")
+    try:
+        dev.set_option("root_mode", 0)
+        sim = engine.DeviceSim(g, od, gd, 0.4, phys)
+        assert sim.n_roots <= 33
+        prev = np.zeros(flat.S, dtype=np.uint32)
+        ms_now = flat.max_speed.copy()
+        for day in range(2):
+            if day == 1:
+                sim.road_construction(flat.adaptable)
+                ms_now, _ = ctwin.road_construction(prev, ms_now, flat.adaptable)
+            sim.step()
+            want, cnt = ctwin.day(csr, ctwin.weights(flat.length, ms_now, prev, 0.4), od, gd, nthreads=16)
+            c = sim.counters()
+            assert c["fallback_sweeps"] == 0 and c["trips_stuck"] == 0 and cnt["stuck"] == 0
+            assert np.array_equal(sim.get_load(), want), day
+            sim.commit_total()
+            prev = want
+        assert c["trips_unreachable"] == 2 * cnt["unreachable"]
+        sim.close()
+    finally:
+        dev.set_option("root_mode", old)
+    g.close()

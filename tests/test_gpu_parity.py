@@ -149,7 +149,10 @@ def test_road_construction_golden(dev, phys):
                                   dict(block_threads=32, near_smem_entries=32, delta_factor=1.0),
                                   # overlapped buckets: off, and so eager that nearly every advance finds entries pending
                                   dict(early_advance=0), dict(early_advance=64, delta_factor=0.5),
-                                  dict(early_advance=64, block_threads=32, near_smem_entries=32)])
+                                  dict(early_advance=64, block_threads=32, near_smem_entries=32),
+                                  # thread-block clusters sharing one group (the large-graph configuration)
+                                  dict(cluster=2, block_threads=512), dict(cluster=8, block_threads=1024),
+                                  dict(cluster=4, block_threads=1024, delta_factor=0.5, early_advance=64)])
 @pytest.mark.parametrize("ranked", [False, True])
 def test_sssp_dist_and_pred_vs_oracle(dev, shape, opts, ranked):
     """Single trees: distances bit-equal to Dijkstra, predecessors equal under the canonical rule;
@@ -413,6 +416,51 @@ def test_queue_overflow_falls_back_to_sweeps(dev, phys, preread):
         d0, p0, _ = ctwin.sssp(ctwin.Csr(V, arr["u"], arr["v"]), w, 5)
         assert np.array_equal(dist.view(np.uint64), d0.view(np.uint64))
         assert np.array_equal(pred, p0)
+        g.close()
+    finally:
+        for k, val in old.items():
+            dev.set_option(k, val)
+
+
+@pytest.mark.parametrize("cluster,block", [(2, 512), (4, 1024), (8, 1024)])
+def test_cluster_shared_groups_day_and_overflow(dev, phys, cluster, block):
+    """The CTAs of a thread-block cluster share one group of trees (frontier queues, far piles and counters in global
+    memory, a cluster barrier per round): a day of 4 k trips over ~60 groups equals the oracle's, the counters add up,
+    and with starved queues the cluster-wide Bellman-Ford safety net still delivers exact distances."""
+    from oracle import ctwin
+    from streets4mpi_b200 import engine, synth
+    arr = synth.grid_arrays(70, 90, seed=17)
+    V = len(arr["node_ids"])
+    rng = np.random.default_rng(8)
+    o = rng.integers(0, V, 4000).astype(np.int32)
+    gl = rng.choice(V, 900, replace=False)[rng.integers(0, 900, 4000)].astype(np.int32)
+    keys = ("cluster", "block_threads", "root_mode", "queue_entries", "delta_factor")
+    old = {k: dev.get_option(k) for k in keys}
+    try:
+        dev.set_option("cluster", cluster)
+        dev.set_option("block_threads", block)
+        dev.set_option("root_mode", 1)
+        g = engine.DeviceGraph(dev, V, arr["u"], arr["v"], arr["length"], arr["max_speed"])
+        sim = engine.DeviceSim(g, o, gl, 0.3, phys)
+        csr = ctwin.Csr(V, arr["u"], arr["v"])
+        prev = np.zeros(len(arr["u"]), dtype=np.uint32)
+        hops = 0
+        for _ in range(2):
+            sim.step()
+            want, cnt = ctwin.day(csr, ctwin.weights(arr["length"], arr["max_speed"], prev, 0.3), gl, o, nthreads=4)
+            assert np.array_equal(sim.get_load(), want)
+            hops += cnt["hops"]
+            sim.commit_total()
+            prev = want
+        c = sim.counters()
+        assert c["fallback_sweeps"] == 0 and c["hops"] == hops and c["trips_routed"] == 8000
+        sim.close()
+        dev.set_option("queue_entries", 16)
+        dev.set_option("delta_factor", 50.0)
+        w = rng.uniform(0.1, 10.0, len(arr["u"]))
+        dist, pred = g.sssp(w, 77)
+        d0, p0, _ = ctwin.sssp(csr, w, 77)
+        assert np.array_equal(dist.view(np.uint64), d0.view(np.uint64)) and np.array_equal(pred, p0)
         g.close()
     finally:
         for k, val in old.items():

@@ -12,6 +12,12 @@ trips), runs two days with the congestion feedback between them and checks
 and reports trees/s, trips/s and the extrapolated day.
 
     python tools/run_cfg5_sample.py [--rows 7071 --cols 7071] [--trees 256] [--trips-per-day 100000000]
+
+--contiguous (default): the sampled origins are a contiguous run of the residential nodes along the locality curve, as
+dense as in the full day (1 % of the nodes), so that the groups of neighbouring trees the SSSP kernel forms look like
+the full day's; --scattered draws them over the whole graph (r1's sample).
+Under torchrun (weak scaling, BASELINE cfg5): every rank takes its own run of origins and its own trips, the daily
+exchange (NCCL all-reduce of the uint32[S] load through the library communicator) is timed, rank 0 prints all ranks.
 """
 import argparse
 import json
@@ -33,7 +39,10 @@ ap.add_argument("--trees", type=int, default=256)
 ap.add_argument("--trips-per-day", type=int, default=100_000_000)
 ap.add_argument("--days", type=int, default=2)
 ap.add_argument("--no-oracle", action="store_true")
+ap.add_argument("--scattered", action="store_true")
+ap.add_argument("--options", default="", help="library options, key=value,...")
 args = ap.parse_args()
+rank_id, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
 
 t0 = time.perf_counter()
 arr = synth.ladder_arrays(args.rows, args.cols, seed=1)
@@ -45,14 +54,27 @@ t_gen = time.perf_counter() - t0
 cats = synth.node_categories(arr["node_ids"], seed=1, goal_fraction=0.02, residential_fraction=0.01)
 residential, goals = cats["residential"], cats["goals"]
 # the day's trips of the sampled origins: every residential origin gets trips_per_day / len(residential) on average
-rng = np.random.default_rng(settings["random_seed"])
-origins = rng.choice(residential, size=min(args.trees, len(residential)), replace=False)
+rng = np.random.default_rng(settings["random_seed"] + 37 * rank_id)
+if args.scattered:
+    origins = rng.choice(residential, size=min(args.trees, len(residential)), replace=False)
+else:
+    along = residential[np.argsort(rank[flat.dense(residential)], kind="stable")]      # residential nodes along the curve
+    n_take = min(args.trees, len(along))
+    start = (len(along) // (world + 1)) * (rank_id + 1) - n_take // 2
+    origins = along[max(0, start): max(0, start) + n_take]
 per_origin = rng.poisson(args.trips_per_day / len(residential), size=len(origins)).clip(min=1)
 o = np.repeat(origins, per_origin).astype(np.int32)
 g = goals[rng.integers(0, len(goals), size=len(o))].astype(np.int32)
 
-dev = engine.default_device()
+dev = engine.Device(int(os.environ.get("LOCAL_RANK", "0")))
+engine.set_default_device(dev)
 dev.set_option("root_mode", 0)                          # residential origins: the reference's own grouping
+for kv in filter(None, args.options.split(",")):
+    k, v = kv.split("=")
+    dev.set_option(k, float(v))
+if world > 1:
+    from streets4mpi_b200 import distributed
+    distributed.init(dev)
 t0 = time.perf_counter()
 graph = engine.DeviceGraph(dev, V, flat.u, flat.v, flat.length, flat.max_speed, node_rank=rank)
 phys = engine.make_physics(settings)
@@ -84,7 +106,10 @@ for day in range(args.days):
                         "relaxations_per_arc": round(c["arcs_relaxed"] / max(1, c["arcs_algorithmic"]), 2),
                         "rounds_per_tree": c["relax_rounds"] // max(1, sim.n_roots),
                         "hops_per_trip": round(c["hops"] / len(o), 1), "properties_ok": bool(ok)})
-    sim.commit_total()
+    t0 = time.perf_counter()
+    sim.exchange()                                      # NCCL all-reduce of uint32[S] (several ranks) + cumulative merge
+    dev.sync()
+    out["days"][-1]["exchange_seconds"] = round(time.perf_counter() - t0, 4)
 full_day = len(residential) / out["days"][-1]["trees_per_sec"]
 out["extrapolated_full_day_seconds_1gpu"] = round(full_day, 1)
 if not args.no_oracle:
@@ -100,4 +125,16 @@ if not args.no_oracle:
     out["oracle_tree"] = {"dist_bit_equal": bool(np.array_equal(dist.view(np.uint64), d0.view(np.uint64))),
                           "pred_equal": bool(np.array_equal(pred, p0)), "cpu_seconds_one_tree": round(t_cpu_tree, 1),
                           "gpu_seconds_one_tree_with_copies": round(t_gpu_tree, 2)}
-print(json.dumps(out))
+out["rank"], out["world"] = rank_id, world
+out["options"] = args.options or "defaults"
+if world > 1:
+    import torch.distributed as dist
+    box = [None] * world
+    dist.all_gather_object(box, out)
+    if rank_id == 0:
+        print(json.dumps({"ranks": box}))
+    dist.barrier()
+    dev.comm_free()
+    dist.destroy_process_group()
+else:
+    print(json.dumps(out))
