@@ -95,7 +95,7 @@ int s4_ctx_create(int device, void *stream, s4_ctx **out);
 int s4_ctx_destroy(s4_ctx *ctx);
 int s4_ctx_sync(s4_ctx *ctx);
 /* Tunables; 0 means "chosen by the library" where noted.
- *   "delta_factor"       near-bucket width in mean street weights (default 3)
+ *   "delta_factor"       near-bucket width in typical (median) street weights (default 1.5)
  *   "adaptive_delta"     1 (default): the width follows the wave (grows on thin waves, shrinks on floods)
  *   "block_threads"      0 (default: from the graph's wave width) | 32 | 64 | 128 | 256 | 512 | 1024
  *   "ctas_per_sm"        0 (default: 1024 threads per SM)
@@ -115,6 +115,16 @@ int s4_ctx_sync(s4_ctx *ctx);
  *                        Read at s4_sim_create.
  *   "lanes"              2 (default): a day's batches alternate between two concurrent launch lanes;
  *                        1: strictly serial kernels (per-kernel timing)
+ *   "group_lanes"        8 (default) | 4: lanes that expand one node for a whole group of trees on one shared
+ *                        frontier (source-batched SSSP); 0: one tree per CTA (the round-1 kernel)
+ *   "group_words"        2 (default) | 1: distance words per lane; trees per group = group_lanes * group_words - 1
+ *   "lag_factor"         1 (default): a node is held back by this multiple of the root-to-root distance of its group
+ *   "min_batches"        4 (default): a day is cut into at least this many (SSSP launch -> walk) batches
+ *   "balance_waves"      1 (default): fewer trees per group when that fills the last wave of a launch
+ *   "cluster"            0 (default: from the number of slots that fit in the pool) | 1 | 2 | 4 | 8: CTAs of a
+ *                        thread-block cluster that share one group (graphs with 10^7 .. 10^8 nodes: fewer slots than SMs)
+ *   "group_log"          1: keep per-group cycles / rounds / expansions of the last day (s4_graph_group_log)
+ *   "delta_factor" counts MEDIAN street weights (the mean follows the 1 km/h streets road construction leaves behind).
  * No option changes a result. */
 int s4_ctx_set_option(s4_ctx *ctx, const char *key, double value);
 int s4_ctx_get_option(s4_ctx *ctx, const char *key, double *value);
@@ -220,6 +230,10 @@ int s4_sim_road_construction(s4_sim *sim, const uint8_t *adaptable);
 int s4_sim_get_max_speed(s4_sim *sim, int32_t *visible_out, int32_t *insertion_out);
 int s4_sim_set_max_speed(s4_sim *sim, const int32_t *visible, const int32_t *insertion_or_null);
 
+/* Diagnostics: the day's root slots as the SSSP kernel consumes them -- consecutive groups of *group_size slots, one
+ * group = the trees that share a frontier, -1 = empty slot; node ids in the caller's numbering.  out may be NULL to
+ * query *n_slots.  Valid after the first s4_sim_step (the group size follows the launch geometry). */
+int s4_sim_get_root_slots(s4_sim *sim, int32_t *out, int64_t cap, int64_t *n_slots, int *group_size);
 int s4_sim_get_counters(s4_sim *sim, s4_counters *out);
 /* Trips whose walk found no predecessor since the last reset (simulation.py:83-85 would raise KeyError there): only
  * possible on a zero-weight plateau of more than 32 nodes.  Cheap (8 bytes D2H behind the stream); the host layer

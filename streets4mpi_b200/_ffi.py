@@ -88,6 +88,7 @@ SIGNATURES = {
     "s4_sim_get_counters": (C.c_int, [_vp, C.POINTER(Counters)]),
     "s4_sim_reset_counters": (C.c_int, [_vp]),
     "s4_sim_trips_stuck": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
+    "s4_sim_get_root_slots": (C.c_int, [_vp, C.POINTER(C.c_int32), C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int)]),
     "s4_driving_speed": (C.c_int, [_vp, C.c_int64, _f64p, _i32p, _u32p, C.POINTER(Physics), _f64p]),
 }
 

@@ -75,6 +75,9 @@ struct Options {
     double lag_factor = 1.0;        // source-batched kernel: hold a node back by this multiple of the root-to-root distance
     int group_log = 0;              // diagnostics: keep per-group cycles / rounds / entries of the last day (s4_graph_group_log)
     int min_batches = 4;            // a day is cut into at least this many (SSSP launch -> walk) batches when lanes = 2
+    int l2_persist = 0;             // 1: keep the fixed-stride arc rows (64 B per node, read by every expansion and every
+                                    // hop) resident in L2 with an access-policy window on both lanes' streams
+    int balance_waves = 1;          // fewer trees per group when that fills the last wave of a launch (few groups per GPU)
     int cluster = 0;                // CTAs of a thread-block cluster that share one group of trees (1 | 2 | 4 | 8); 0 = from
                                     // the number of slots that fit in the pool (large graphs: fewer slots than SMs)
 };
@@ -107,6 +110,7 @@ struct s4_ctx {
     void *stage_dev = nullptr;
     size_t stage_bytes = 0;
     int comm_ranks = 1, comm_rank = 0;
+    bool l2_limit_set = false, l2_window_on = false;
 };
 
 // NCCL entry points, bound at run time (see "rank-level exchange" below)
@@ -160,6 +164,7 @@ struct s4_graph {
     std::vector<int32_t> max_speed0;   // host copy of the uploaded limits
     std::vector<u32> row_ptr_h, col_h;  // host copy of the CSR (device numbering): root clustering at simulation setup
     std::vector<u32> gorder_h, ginv_h;  // grouping order of tree roots: device number -> position / position -> device number
+    std::vector<int32_t> ecc_h;         // hops to the farther end of the graph's longest BFS path (depth of a tree rooted here)
     DevBuf<u32> gorder, ginv;
     // connected components (host): algorithmic arcs / nodes of a tree rooted at r
     std::vector<int32_t> comp_of;
@@ -205,6 +210,8 @@ struct s4_sim {
     // ... and as the kernels consume them: roots clustered into groups of `grouped_K` trees (slots padded with -1),
     // trips in the order of those slots
     int grouped_K = 0;
+    int grouped_fill = 0;          // trees actually put into a group (<= grouped_K)
+    bool grouped_longest_first = false;
     int64_t Dp = 0;                // slots = groups * grouped_K
     DevBuf<int32_t> trip_target;   // T
     DevBuf<u32> trip_root;         // T, index into roots
@@ -327,7 +334,8 @@ static void option_slot(Options &o, const char *key, int *kind, void **raw)
         {"walk_ell", 1, &o.walk_ell},                {"group_lanes", 1, &o.group_lanes},
         {"group_words", 1, &o.group_words},         {"lag_factor", 0, &o.lag_factor},
         {"min_batches", 1, &o.min_batches},         {"group_log", 1, &o.group_log},
-        {"cluster", 1, &o.cluster},
+        {"cluster", 1, &o.cluster},                 {"balance_waves", 1, &o.balance_waves},
+        {"l2_persist", 1, &o.l2_persist},
     };
     for (auto &it : items)
         if (strcmp(it.k, key) == 0) { *kind = it.kind; *raw = it.p; return; }
@@ -357,7 +365,8 @@ extern "C" int s4_ctx_set_option(s4_ctx *ctx, const char *key, double value)
               t.early_advance >= 0 && t.early_advance <= 64 && (t.walk_ell == 0 || t.walk_ell == 1) &&
               (t.group_lanes == 0 || t.group_lanes == 4 || t.group_lanes == 8) && (t.group_words == 1 || t.group_words == 2) &&
               t.lag_factor >= 0.0 && t.lag_factor <= 64.0 && t.min_batches >= 1 && t.min_batches <= 64 &&
-              (t.cluster == 0 || t.cluster == 1 || t.cluster == 2 || t.cluster == 4 || t.cluster == 8);
+              (t.cluster == 0 || t.cluster == 1 || t.cluster == 2 || t.cluster == 4 || t.cluster == 8) &&
+              (t.l2_persist == 0 || t.l2_persist == 1) && (t.balance_waves == 0 || t.balance_waves == 1);
     if (!ok) return fail(S4_ERR_ARG, "option '%s': value %g out of range", key, value);
     ctx->opt = trial;
     return S4_OK;
@@ -660,6 +669,10 @@ extern "C" int s4_graph_upload(s4_ctx *ctx, int32_t V, int64_t S, const int32_t 
             int32_t dummy = 0;
             bfs(far2, &dummy, &reached);
             std::vector<int32_t> db(level);
+            // how deep a tree rooted at a node is, in hops (the two ends of the longest BFS path bound it from below):
+            // groups of trees are started longest-first when a launch has only a few waves of them
+            g->ecc_h.resize((size_t)V);
+            for (int32_t i = 0; i < V; ++i) g->ecc_h[(size_t)i] = std::max(0, std::max(da[(size_t)i], db[(size_t)i]));
             int32_t c_node = far1;
             int32_t best_min = -1;
             for (int32_t i = 0; i < V; ++i) {
@@ -1252,8 +1265,10 @@ static int sim_group(s4_sim *sim, DevBuf<u32> &kin, DevBuf<u32> &vin)
 // the graph; a breadth-first search from an unassigned seed collects the unassigned roots it meets until it has K of
 // them or has visited 6 * K * V / D nodes (six times the ball that holds K roots on average); smaller groups are
 // padded with -1.  O(V) node visits in total.
-static void cluster_roots(const s4_graph *g, const std::vector<int32_t> &roots, int K, std::vector<int32_t> &slots,
-                          std::vector<int64_t> &slot_of)
+// K_fill <= K: roots collected per group (the rest of its K slots stays empty): fewer trees per group when that
+// evens out the last wave of the launch (see s4_sim_step).
+static void cluster_roots(const s4_graph *g, const std::vector<int32_t> &roots, int K, int K_fill, bool longest_first,
+                          std::vector<int32_t> &slots, std::vector<int64_t> &slot_of)
 {
     const int64_t D = (int64_t)roots.size(), V = g->V;
     slots.clear();
@@ -1266,7 +1281,8 @@ static void cluster_roots(const s4_graph *g, const std::vector<int32_t> &roots, 
     std::vector<int32_t> level((size_t)V, -1), queue, touched;
     std::vector<int64_t> root_idx((size_t)V, -1);                   // node -> index among the roots while unassigned
     for (int64_t i = 0; i < D; ++i) root_idx[(size_t)roots[(size_t)i]] = i;
-    const int64_t cap = std::max<int64_t>(64, 6 * (int64_t)K * V / std::max<int64_t>(1, D));
+    const int64_t cap = std::max<int64_t>(64, 6 * (int64_t)K_fill * V / std::max<int64_t>(1, D));
+    std::vector<int64_t> score;                                     // per group: expected duration (hops)
     for (int64_t i = 0; i < D; ++i) {
         const int32_t seed = roots[(size_t)i];
         if (root_idx[(size_t)seed] < 0) continue;                   // already in a group
@@ -1278,10 +1294,12 @@ static void cluster_roots(const s4_graph *g, const std::vector<int32_t> &roots, 
         level[(size_t)seed] = 0;
         touched.push_back(seed);
         int got = 0;
-        for (size_t head = 0; head < queue.size() && got < K && (int64_t)head <= cap; ++head) {
+        int32_t radius = 0;                                         // hops from the seed to the farthest root of the group
+        for (size_t head = 0; head < queue.size() && got < K_fill && (int64_t)head <= cap; ++head) {
             const int32_t x = queue[head];
             const int64_t ri = root_idx[(size_t)x];
             if (ri >= 0) {
+                radius = level[(size_t)x];
                 root_idx[(size_t)x] = -1;
                 slot_of[(size_t)ri] = (int64_t)(base + (size_t)got);
                 slots[base + (size_t)got++] = x;
@@ -1292,12 +1310,35 @@ static void cluster_roots(const s4_graph *g, const std::vector<int32_t> &roots, 
             }
         }
         for (int32_t x : touched) level[(size_t)x] = -1;
+        // a tree is as deep as its root is far from the far end of the graph; a spread-out group waits for its slowest tree
+        score.push_back((g->ecc_h.empty() ? 0 : (int64_t)g->ecc_h[(size_t)seed]) + 2 * (int64_t)radius);
+    }
+    if (longest_first && !score.empty()) {
+        // few waves of groups per launch: start the long ones first, so that the last wave is made of short ones
+        const int64_t G = (int64_t)score.size();
+        std::vector<int64_t> order((size_t)G);
+        std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return score[(size_t)a] > score[(size_t)b]; });
+        std::vector<int32_t> sorted(slots.size());
+        std::vector<int64_t> new_pos((size_t)G);
+        for (int64_t p = 0; p < G; ++p) {
+            new_pos[(size_t)order[(size_t)p]] = p;
+            std::copy(slots.begin() + order[(size_t)p] * K, slots.begin() + (order[(size_t)p] + 1) * K, sorted.begin() + p * K);
+        }
+        slots.swap(sorted);
+        for (int64_t i = 0; i < D; ++i) {
+            const int64_t s_old = slot_of[(size_t)i];
+            slot_of[(size_t)i] = new_pos[(size_t)(s_old / K)] * K + s_old % K;
+        }
     }
 }
 
 // (re)build the arrays the kernels consume for groups of K trees
-static int sim_regroup(s4_sim *sim, int K)
+static int sim_regroup(s4_sim *sim, int K, int K_fill = 0, bool longest_first = false)
 {
+    if (K_fill <= 0 || K_fill > K) K_fill = K;
+    sim->grouped_fill = K_fill;
+    sim->grouped_longest_first = longest_first;
     s4_graph *g = sim->g;
     s4_ctx *ctx = g->ctx;
     cudaStream_t st = ctx->stream;
@@ -1310,7 +1351,7 @@ static int sim_regroup(s4_sim *sim, int K)
     }
     std::vector<int32_t> slots;
     std::vector<int64_t> slot_of;
-    cluster_roots(g, sim->h_roots0, K, slots, slot_of);
+    cluster_roots(g, sim->h_roots0, K, K_fill, longest_first, slots, slot_of);
     const int64_t Dp = (int64_t)slots.size();
     sim->Dp = Dp;
     // trips of slot j start at h_root_off[j]; empty for padding slots
@@ -1470,6 +1511,27 @@ extern "C" int s4_sim_get_trips(s4_sim *sim, int32_t *origin_out, int32_t *goal_
     return S4_OK;
 }
 
+// Diagnostics: the root slots of the day as the SSSP kernel consumes them (groups of K slots, -1 = empty), caller's ids.
+extern "C" int s4_sim_get_root_slots(s4_sim *sim, int32_t *out, int64_t cap, int64_t *n_slots, int *group_size)
+{
+    CHECK_ARG(sim && n_slots, "s4_sim_get_root_slots: NULL argument");
+    s4_graph *g = sim->g;
+    CU(cudaSetDevice(g->ctx->device));
+    *n_slots = sim->Dp;
+    if (group_size) *group_size = sim->grouped_K;
+    if (!out || sim->Dp == 0) return S4_OK;
+    CHECK_ARG(cap >= sim->Dp, "s4_sim_get_root_slots: buffer too small");
+    CU(cudaMemcpyAsync(out, sim->roots.p, (size_t)sim->Dp * sizeof(int32_t), cudaMemcpyDeviceToHost, g->ctx->stream));
+    CU(cudaStreamSynchronize(g->ctx->stream));
+    if (!g->rank.empty()) {
+        std::vector<int32_t> inv((size_t)g->V);
+        for (int32_t i = 0; i < g->V; ++i) inv[(size_t)g->rank[(size_t)i]] = i;
+        for (int64_t i = 0; i < sim->Dp; ++i)
+            if (out[i] >= 0) out[i] = inv[(size_t)out[i]];
+    }
+    return S4_OK;
+}
+
 static void free_events(std::vector<EvPair> &v)
 {
     for (auto &e : v) {
@@ -1616,7 +1678,21 @@ extern "C" int s4_sim_step(s4_sim *sim)
     SsspLaunch L;
     if ((rc = plan_sssp(g, &L))) return rc;
     const int64_t K = L.lay.K;
-    if (sim->grouped_K != (int)K && (rc = sim_regroup(sim, (int)K))) return rc;   // the group size changed since the trips were set up
+    // Trees per group.  A launch runs L.units() groups at a time; when the day has only a few waves of groups (several
+    // GPUs sharing a day), a partly filled last wave costs a whole group time: then the groups take fewer trees, so
+    // that their number fills whole waves (4 % head room: the greedy clustering leaves some groups short).
+    int K_fill = (int)K;
+    if (K > 1 && sim->D > 0 && ctx->opt.balance_waves) {
+        const int64_t W = std::max(1, L.units());
+        const int64_t G0 = (sim->D + K - 1) / K, waves = (G0 + W - 1) / W;
+        const double target = 0.96 * (double)(waves * W);
+        K_fill = (int)std::min<int64_t>(K, std::max<int64_t>(1, (int64_t)std::ceil((double)sim->D / std::max(1.0, target))));
+    }
+    // ... and with at most four waves of groups in the whole day they are started longest-first (expected depth of the
+    // trees + spread of the group), all in one launch per lane-slot, so that the work queue packs the waves
+    const bool few_waves = K > 1 && ctx->opt.balance_waves && (sim->D + K_fill - 1) / K_fill <= 4 * (int64_t)std::max(1, L.units());
+    if ((sim->grouped_K != (int)K || sim->grouped_fill != K_fill || sim->grouped_longest_first != few_waves) &&
+        (rc = sim_regroup(sim, (int)K, K_fill, few_waves))) return rc;
     const int64_t D = sim->Dp;                                     // root slots (groups padded to K)
     const int64_t G = D / K;                                       // slots of the distance pool the day needs
     if (D > 0 && (rc = ensure_scratch(g, L, G))) return rc;
@@ -1635,7 +1711,10 @@ extern "C" int s4_sim_step(s4_sim *sim)
     const int64_t slots = std::max<int64_t>(1, g->pool_slots);
     const bool split = ctx->opt.lanes >= 2 && slots >= 2 && G >= 2;
     int64_t B = split ? slots / 2 : slots;                         // slots per launch
-    if (split) B = std::min(B, std::max<int64_t>(1, (G + ctx->opt.min_batches - 1) / ctx->opt.min_batches));
+    // a launch should hold at least two waves of groups (the work queue then packs them); more launches only when
+    // the day is long enough for the walk of one batch to hide under the SSSP of the next
+    if (split) B = std::min(B, std::max<int64_t>(std::max<int64_t>(1, (G + ctx->opt.min_batches - 1) / ctx->opt.min_batches),
+                                                  ctx->opt.balance_waves ? 2 * (int64_t)std::max(1, L.units()) : 1));
     const int64_t n_batches = G > 0 ? (G + B - 1) / B : 0;
     g->glog_groups = 0;
     if (ctx->opt.group_log && L.gfn && G > 0) {
@@ -1649,6 +1728,27 @@ extern "C" int s4_sim_step(s4_sim *sim)
         CU(sim->deferred.ensure((size_t)std::max<int64_t>(sim->T, 1)));
         CU(sim->deferred_counts.ensure((size_t)std::max<int64_t>(n_batches, 1024)));
         CU(cudaMemsetAsync(sim->deferred_counts.p, 0, sim->deferred_counts.n * sizeof(u32), st));
+    }
+    // optional: the arc rows stay in L2 (persisting access-policy window; the distance rows stream through the rest)
+    {
+        cudaStreamAttrValue av = {};
+        if (ctx->opt.l2_persist && sim->ellw.p) {
+            const size_t bytes = (size_t)g->V * kEllWidth * sizeof(Arc);
+            const size_t max_persist = (size_t)ctx->prop.persistingL2CacheMaxSize, max_win = (size_t)ctx->prop.accessPolicyMaxWindowSize;
+            if (max_persist > 0 && max_win > 0) {
+                if (!ctx->l2_limit_set) { CU(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, max_persist)); ctx->l2_limit_set = true; }
+                av.accessPolicyWindow.base_ptr = (void *)sim->ellw.p;
+                av.accessPolicyWindow.num_bytes = std::min(bytes, max_win);
+                av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)max_persist / (double)std::min(bytes, max_win));
+                av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            }
+        }
+        if (ctx->opt.l2_persist || ctx->l2_window_on) {
+            CU(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av));
+            CU(cudaStreamSetAttribute(ctx->walk_stream, cudaStreamAttributeAccessPolicyWindow, &av));
+            ctx->l2_window_on = ctx->opt.l2_persist != 0;
+        }
     }
     if (split) {                                                   // lane 1 starts after K1 and the counter reset
         CU(cudaEventRecord(ctx->sssp_done[0], st));

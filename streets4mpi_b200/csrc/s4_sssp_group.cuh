@@ -477,20 +477,38 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024
             const u32 fo = f ^ 1u;
             const u32 src_off = 2u * gcap + f * fcap;
             const GroupPushTarget tg = target(b, fo);
-            for (u32 base = 0; base < nf; base += BLOCK * (u32)CL) {
-                const u32 i = base + crank * BLOCK + tid;
-                u32 k1 = 0u, v1 = 0u, key1 = 0u;
-                if (i < nf) {
-                    if constexpr (CL > 1) { v1 = __ldcg(wv + src_off + i); key1 = __ldcg(wk + src_off + i); }
-                    else { v1 = __ldcs(wv + src_off + i); key1 = __ldcs(wk + src_off + i); }
-                    if (key1 <= thr_hi) {
-                        // admitted: unless the node is already queued for the coming round
-                        const u32 old = atomicExch(reinterpret_cast<u32 *>(rows + (size_t)v1 * RW + K), rid);
-                        if (old != rid) k1 = 1u; else ++c_dup;
-                    } else k1 = 2u;
+            // four entries per thread and step, their loads (and the stamps of the admitted ones) in flight together:
+            // with heavy-tailed weights (streets adapted down to 1 km/h) the pile holds many distant entries that are
+            // re-filed at every advance, and a step is one memory round trip
+            constexpr u32 SPLIT = 4;
+            for (u32 base = 0; base < nf; base += BLOCK * (u32)CL * SPLIT) {
+                u32 kx[SPLIT], vx[SPLIT], keyx[SPLIT];
+#pragma unroll
+                for (u32 s4 = 0; s4 < SPLIT; ++s4) {
+                    const u32 i = base + (s4 * (u32)CL + crank) * BLOCK + tid;
+                    kx[s4] = 0u; vx[s4] = 0u; keyx[s4] = 0u;
+                    if (i < nf) {
+                        if constexpr (CL > 1) { vx[s4] = __ldcg(wv + src_off + i); keyx[s4] = __ldcg(wk + src_off + i); }
+                        else { vx[s4] = __ldcs(wv + src_off + i); keyx[s4] = __ldcs(wk + src_off + i); }
+                        kx[s4] = 2u;
+                    }
                 }
-                // the round after this reads (b, c); kept entries go to the other pile (never more than nf)
-                warp_push_g(k1, v1, key1, lane, tg, CNT(c), FAR_CNT(fo), FAR_MIN(fo), OVERFLOW(), c_push);
+                u32 oldx[SPLIT];
+#pragma unroll
+                for (u32 s4 = 0; s4 < SPLIT; ++s4) {
+                    oldx[s4] = rid;
+                    // admitted: unless the node is already queued for the coming round
+                    if (kx[s4] != 0u && keyx[s4] <= thr_hi) {
+                        oldx[s4] = atomicExch(reinterpret_cast<u32 *>(rows + (size_t)vx[s4] * RW + K), rid);
+                        kx[s4] = 1u;
+                    }
+                }
+#pragma unroll
+                for (u32 s4 = 0; s4 < SPLIT; ++s4) {
+                    if (kx[s4] == 1u && oldx[s4] == rid) { kx[s4] = 0u; ++c_dup; }
+                    // the round after this reads (b, c); kept entries go to the other pile (never more than nf)
+                    warp_push_g(kx[s4], vx[s4], keyx[s4], lane, tg, CNT(c), FAR_CNT(fo), FAR_MIN(fo), OVERFLOW(), c_push);
+                }
             }
             sync_all();
             if (lead) { *FAR_CNT(f) = 0u; *FAR_MIN(f) = 0xFFFFFFFFu; }

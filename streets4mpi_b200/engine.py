@@ -320,6 +320,14 @@ class DeviceSim(object):
         check(self.lib.s4_sim_set_max_speed(self._h, ptr(vis, C.c_int32),
                                             None if ins is None else ptr(ins, C.c_int32)))
 
+    def root_slots(self):
+        """(slots int32[groups * K], K): the day's roots as the SSSP kernel groups them, -1 = empty slot (diagnostics)."""
+        n, k = C.c_int64(), C.c_int()
+        check(self.lib.s4_sim_get_root_slots(self._h, None, 0, C.byref(n), C.byref(k)))
+        out = np.empty(max(1, n.value), dtype=np.int32)
+        check(self.lib.s4_sim_get_root_slots(self._h, ptr(out, C.c_int32), n.value, C.byref(n), C.byref(k)))
+        return out[: n.value], int(k.value)
+
     def trips_stuck(self):
         n = C.c_uint64()
         check(self.lib.s4_sim_trips_stuck(self._h, C.byref(n)))

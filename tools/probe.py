@@ -20,6 +20,7 @@ ap.add_argument("--days", type=int, default=2)
 ap.add_argument("--morton", type=int, default=0)
 ap.add_argument("--rank", type=int, default=1)
 ap.add_argument("--goals", type=int, default=0, help="1: the trees are rooted at the cfg3 goal sample (2 %% of the nodes), like a bench day")
+ap.add_argument("--share", type=int, default=0, help="N: keep the first of N contiguous runs of the goals along the locality curve (one GPU's share of an N-GPU day)")
 args = ap.parse_args()
 
 dev = engine.default_device()
@@ -47,6 +48,11 @@ origins = rng.choice(arr["node_ids"], size=args.roots, replace=False)
 goals = cats["goals"][rng.integers(0, len(cats["goals"]), size=args.roots)]
 if args.goals:
     goals = cats["goals"] if args.roots <= 0 else cats["goals"][: args.roots]
+    if args.share > 1:
+        curve = synth.network_from(arr).flat().locality_rank()
+        along = cats["goals"][np.argsort(curve[cats["goals"]], kind="stable")]
+        n = len(along) // args.share
+        goals = along[3 * n: 4 * n] if args.share >= 4 else along[:n]
     origins = rng.choice(arr["node_ids"], size=len(goals))
     dev.set_option("root_mode", 1)
 phys = engine.make_physics(settings)
