@@ -117,7 +117,8 @@ int s4_ctx_sync(s4_ctx *ctx);
  *                        1: strictly serial kernels (per-kernel timing)
  *   "group_lanes"        8 (default) | 4: lanes that expand one node for a whole group of trees on one shared
  *                        frontier (source-batched SSSP); 0: one tree per CTA (the round-1 kernel)
- *   "group_words"        2 (default) | 1: distance words per lane; trees per group = group_lanes * group_words - 1
+ *   "group_words"        0 (default: 4 when twice as many slots as SMs fit in the pool, else 2) | 1 | 2 | 4: distance
+ *                        words per lane; trees per group = group_lanes * group_words - 1 (7 | 15 | 31)
  *   "lag_factor"         1 (default): a node is held back by this multiple of the root-to-root distance of its group
  *   "min_batches"        4 (default): a day is cut into at least this many (SSSP launch -> walk) batches
  *   "balance_waves"      1 (default): fewer trees per group when that fills the last wave of a launch

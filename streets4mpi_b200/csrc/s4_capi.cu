@@ -71,7 +71,8 @@ struct Options {
     int preread = 2;                // 1: filtering read, then returning atomicMin;
                                     // 2: filtering read decides the push, minimum sent as RED (no wait)
     int group_lanes = 8;            // lanes that expand one node for a whole group of trees (4 | 8); 0: one tree per CTA
-    int group_words = 2;            // distance words per lane (1 | 2): trees per group = group_lanes * group_words - 1
+    int group_words = 0;            // distance words per lane (1 | 2 | 4): trees per group = group_lanes * group_words - 1;
+                                    // 0 = 4 (31 trees, rows of 256 bytes) when twice as many slots as SMs fit in the pool, else 2
     double lag_factor = 1.0;        // source-batched kernel: hold a node back by this multiple of the root-to-root distance
     int group_log = 0;              // diagnostics: keep per-group cycles / rounds / entries of the last day (s4_graph_group_log)
     int min_batches = 4;            // a day is cut into at least this many (SSSP launch -> walk) batches when lanes = 2
@@ -87,10 +88,10 @@ struct Layout {
     int K = 1;       // trees per slot
     int RW = 1;      // words per node row
 };
-static Layout layout_of(const Options &o)
+static Layout layout_of(const Options &o, int words)
 {
     Layout l;
-    if (o.group_lanes > 0) { l.RW = o.group_lanes * o.group_words; l.K = l.RW - 1; }
+    if (o.group_lanes > 0) { l.RW = o.group_lanes * words; l.K = l.RW - 1; }
     return l;
 }
 
@@ -171,6 +172,7 @@ struct s4_graph {
     std::vector<int64_t> comp_arcs, comp_nodes;
     int auto_block = 256;      // CTA width chosen from the graph's shape (see graph upload)
     int auto_walk_tile = 8;    // lanes per walking trip
+    int auto_words = 0;        // distance words per lane chosen for this graph (0 = not decided yet)
     // scratch shared by every simulation on this graph (sized lazily)
     DevBuf<u64> pool;          // slots * V
     int64_t pool_slots = 0;
@@ -211,6 +213,7 @@ struct s4_sim {
     // trips in the order of those slots
     int grouped_K = 0;
     int grouped_fill = 0;          // trees actually put into a group (<= grouped_K)
+    int grouped_fill0 = -1;        // ... as first computed from the launch geometry (before the whole-wave correction)
     bool grouped_longest_first = false;
     int64_t Dp = 0;                // slots = groups * grouped_K
     DevBuf<int32_t> trip_target;   // T
@@ -363,7 +366,8 @@ extern "C" int s4_ctx_set_option(s4_ctx *ctx, const char *key, double value)
               (t.walk_tile == 0 || t.walk_tile == 4 || t.walk_tile == 8 || t.walk_tile == 16 || t.walk_tile == 32) &&
               (t.preread == 1 || t.preread == 2) && (t.lanes == 1 || t.lanes == 2) &&
               t.early_advance >= 0 && t.early_advance <= 64 && (t.walk_ell == 0 || t.walk_ell == 1) &&
-              (t.group_lanes == 0 || t.group_lanes == 4 || t.group_lanes == 8) && (t.group_words == 1 || t.group_words == 2) &&
+              (t.group_lanes == 0 || t.group_lanes == 4 || t.group_lanes == 8) &&
+              (t.group_words == 0 || t.group_words == 1 || t.group_words == 2 || (t.group_words == 4 && t.group_lanes != 4)) &&
               t.lag_factor >= 0.0 && t.lag_factor <= 64.0 && t.min_batches >= 1 && t.min_batches <= 64 &&
               (t.cluster == 0 || t.cluster == 1 || t.cluster == 2 || t.cluster == 4 || t.cluster == 8) &&
               (t.l2_persist == 0 || t.l2_persist == 1) && (t.balance_waves == 0 || t.balance_waves == 1);
@@ -822,6 +826,7 @@ static GroupKernel pick_group(int block, int lanes, int words, int cl)
         if (block == 512) return cl == 2 ? sssp_group_kernel<512, 8, 2, 2> : cl == 4 ? sssp_group_kernel<512, 8, 2, 4> : sssp_group_kernel<512, 8, 2, 8>;
         return nullptr;
     }
+    if (lanes == 8 && words == 4) return pick_group_block<8, 4>(block);
     if (lanes == 8 && words == 1) return pick_group_block<8, 1>(block);
     if (lanes == 8 && words == 2) return pick_group_block<8, 2>(block);
     if (lanes == 4 && words == 1) return pick_group_block<4, 1>(block);
@@ -863,10 +868,33 @@ static int scratch_budget(s4_graph *g, double *pool_budget, double *ws_budget)
     return S4_OK;
 }
 
+// Trees per group.  A group of 31 (four words per lane, rows of 256 bytes) costs 1.65x the time of a group of 15 on cfg3:
+// 20 % less SM time per tree.  It needs twice the pool per slot, so it is taken when both lanes can still hold a slot
+// per SM; larger graphs keep 15 (and, beyond that, clusters).  Decided once per graph and option setting.
+static int group_words_for(s4_graph *g)
+{
+    const Options &o = g->ctx->opt;
+    if (o.group_lanes == 0) return 1;
+    if (o.group_words > 0) return o.group_words;
+    if (o.group_lanes != 8) return 2;
+    if (g->auto_words == 0) {
+        double pool_budget = 0.0, ws_budget = 0.0;
+        g->auto_words = 2;
+        if (scratch_budget(g, &pool_budget, &ws_budget) == S4_OK) {
+            const double per_slot = 8.0 * (double)g->V * 32.0;
+            const double slots = o.batch_roots > 0 ? (double)(o.batch_roots / 31) : pool_budget / per_slot;
+            if (slots >= 2.0 * (double)g->ctx->prop.multiProcessorCount) g->auto_words = 4;
+        }
+    }
+    return g->auto_words;
+}
+static Layout layout_for(s4_graph *g) { return layout_of(g->ctx->opt, group_words_for(g)); }
+
 static int plan_sssp(s4_graph *g, SsspLaunch *L)
 {
     const Options &o = g->ctx->opt;
-    L->lay = layout_of(o);
+    L->lay = layout_for(g);
+    const int words = group_words_for(g);
     const bool grouped = o.group_lanes > 0;
     // CTA width from the graph's wave width (graph upload): a tree keeps about `auto_block` nodes in flight per
     // relaxation round; the source-batched kernel spends group_lanes lanes on every node it expands
@@ -885,7 +913,7 @@ static int plan_sssp(s4_graph *g, SsspLaunch *L)
         if (!o.block_threads)
             while (block < 1024 && (int64_t)sms * std::min(32, 1024 / block) > per_lane) block *= 2;
         // fewer slots than SMs (10^7 .. 10^8 nodes): the CTAs of a cluster share a group
-        if (grouped && o.group_lanes == 8 && o.group_words == 2 && block >= 512) {
+        if (grouped && o.group_lanes == 8 && words == 2 && block >= 512) {
             if (o.cluster > 0) cl = o.cluster;
             else while (cl < 8 && per_lane * (cl * 2) * (1024 / block) <= (int64_t)sms) cl *= 2;
         }
@@ -894,9 +922,9 @@ static int plan_sssp(s4_graph *g, SsspLaunch *L)
     const int ctas = o.ctas_per_sm ? o.ctas_per_sm : std::min(32, std::max(1, 1024 / block));
     L->cl = cl;
     if (grouped) {
-        L->gfn = pick_group(block, o.group_lanes, o.group_words, cl);
+        L->gfn = pick_group(block, o.group_lanes, words, cl);
         L->fn = nullptr;
-        if (!L->gfn) return fail(S4_ERR_ARG, "no source-batched SSSP kernel for block=%d lanes=%d words=%d cluster=%d", block, o.group_lanes, o.group_words, cl);
+        if (!L->gfn) return fail(S4_ERR_ARG, "no source-batched SSSP kernel for block=%d lanes=%d words=%d cluster=%d", block, o.group_lanes, words, cl);
     } else {
         L->fn = pick_sssp(block);
         L->gfn = nullptr;
@@ -1279,56 +1307,111 @@ static void cluster_roots(const s4_graph *g, const std::vector<int32_t> &roots, 
         return;
     }
     std::vector<int32_t> level((size_t)V, -1), queue, touched;
-    std::vector<int64_t> root_idx((size_t)V, -1);                   // node -> index among the roots while unassigned
-    for (int64_t i = 0; i < D; ++i) root_idx[(size_t)roots[(size_t)i]] = i;
-    const int64_t cap = std::max<int64_t>(64, 6 * (int64_t)K_fill * V / std::max<int64_t>(1, D));
-    std::vector<int64_t> score;                                     // per group: expected duration (hops)
+    std::vector<int64_t> idx_of((size_t)V, -1);                     // node -> index among the roots
+    std::vector<int32_t> group_of((size_t)V, -1);                   // root node -> its group once assigned
+    for (int64_t i = 0; i < D; ++i) idx_of[(size_t)roots[(size_t)i]] = i;
+    auto bfs_reset = [&]() { for (int32_t x : touched) level[(size_t)x] = -1; queue.clear(); touched.clear(); };
+    auto bfs_push = [&](int32_t y, int32_t lv) { level[(size_t)y] = lv; queue.push_back(y); touched.push_back(y); };
+    auto expand = [&](int32_t x) {
+        for (u32 e = g->row_ptr_h[(size_t)x]; e < g->row_ptr_h[(size_t)x + 1]; ++e) {
+            const int32_t y = (int32_t)g->col_h[e];
+            if (level[(size_t)y] < 0) bfs_push(y, level[(size_t)x] + 1);
+        }
+    };
+    // How many nodes a search visits before it has collected K_fill roots.  With every group filled to the brim
+    // (spare == false) the estimate is the global density, as in a whole day on one GPU.  When the groups keep spare
+    // slots (one GPU's share of a day: the roots cover part of the graph only, at the day's density) it is measured on
+    // a sample of seeds, the search stops at twice that ball, and what it leaves behind -- scattered roots that would
+    // otherwise be swept into wide, slow groups -- joins the nearest group that still has room.
+    const bool spare = K_fill * 5 <= K * 4;
+    int64_t cap = std::max<int64_t>(64, 6 * (int64_t)K_fill * V / std::max<int64_t>(1, D));
+    if (spare) {
+        std::vector<int64_t> balls;
+        const int64_t step = std::max<int64_t>(1, D / 48);
+        for (int64_t i = 0; i < D && balls.size() < 48; i += step) {
+            bfs_push(roots[(size_t)i], 0);
+            int got = 0;
+            size_t head = 0;
+            for (; head < queue.size() && got < K_fill; ++head) {
+                const int32_t x = queue[head];
+                if (idx_of[(size_t)x] >= 0) ++got;
+                expand(x);
+            }
+            balls.push_back((int64_t)head);
+            bfs_reset();
+        }
+        std::nth_element(balls.begin(), balls.begin() + balls.size() / 2, balls.end());
+        cap = std::max<int64_t>(64, 2 * balls[balls.size() / 2]);
+    }
+    std::vector<std::vector<int32_t>> members;
+    std::vector<int32_t> seed_of, radius_of;
     for (int64_t i = 0; i < D; ++i) {
         const int32_t seed = roots[(size_t)i];
-        if (root_idx[(size_t)seed] < 0) continue;                   // already in a group
-        const size_t base = slots.size();
-        slots.resize(base + (size_t)K, -1);
-        queue.clear();
-        touched.clear();
-        queue.push_back(seed);
-        level[(size_t)seed] = 0;
-        touched.push_back(seed);
-        int got = 0;
+        if (group_of[(size_t)seed] >= 0) continue;                  // already in a group
+        const int32_t gid = (int32_t)members.size();
+        members.emplace_back();
+        std::vector<int32_t> &mem = members.back();
+        bfs_push(seed, 0);
         int32_t radius = 0;                                         // hops from the seed to the farthest root of the group
-        for (size_t head = 0; head < queue.size() && got < K_fill && (int64_t)head <= cap; ++head) {
+        for (size_t head = 0; head < queue.size() && (int)mem.size() < K_fill && (int64_t)head <= cap; ++head) {
             const int32_t x = queue[head];
-            const int64_t ri = root_idx[(size_t)x];
-            if (ri >= 0) {
+            if (idx_of[(size_t)x] >= 0 && group_of[(size_t)x] < 0) {
                 radius = level[(size_t)x];
-                root_idx[(size_t)x] = -1;
-                slot_of[(size_t)ri] = (int64_t)(base + (size_t)got);
-                slots[base + (size_t)got++] = x;
+                group_of[(size_t)x] = gid;
+                mem.push_back(x);
             }
-            for (u32 e = g->row_ptr_h[(size_t)x]; e < g->row_ptr_h[(size_t)x + 1]; ++e) {
-                const int32_t y = (int32_t)g->col_h[e];
-                if (level[(size_t)y] < 0) { level[(size_t)y] = level[(size_t)x] + 1; queue.push_back(y); touched.push_back(y); }
-            }
+            expand(x);
         }
-        for (int32_t x : touched) level[(size_t)x] = -1;
-        // a tree is as deep as its root is far from the far end of the graph; a spread-out group waits for its slowest tree
-        score.push_back((g->ecc_h.empty() ? 0 : (int64_t)g->ecc_h[(size_t)seed]) + 2 * (int64_t)radius);
+        bfs_reset();
+        seed_of.push_back(seed);
+        radius_of.push_back(radius);
     }
-    if (longest_first && !score.empty()) {
-        // few waves of groups per launch: start the long ones first, so that the last wave is made of short ones
-        const int64_t G = (int64_t)score.size();
-        std::vector<int64_t> order((size_t)G);
+    if (spare) {
+        // groups less than half full are dissolved, smallest first: each of their roots joins the nearest group that is
+        // at least half full and has a free slot (within four search balls), or stays
+        std::vector<int32_t> order(members.size());
         std::iota(order.begin(), order.end(), 0);
-        std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return score[(size_t)a] > score[(size_t)b]; });
-        std::vector<int32_t> sorted(slots.size());
-        std::vector<int64_t> new_pos((size_t)G);
-        for (int64_t p = 0; p < G; ++p) {
-            new_pos[(size_t)order[(size_t)p]] = p;
-            std::copy(slots.begin() + order[(size_t)p] * K, slots.begin() + (order[(size_t)p] + 1) * K, sorted.begin() + p * K);
+        std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return members[(size_t)x].size() < members[(size_t)y].size(); });
+        for (int32_t gid : order) {
+            if ((int)members[(size_t)gid].size() * 2 > K_fill) break;
+            std::vector<int32_t> keep;
+            for (int32_t r : members[(size_t)gid]) {
+                bfs_push(r, 0);
+                int32_t target = -1;
+                for (size_t head = 0; head < queue.size() && (int64_t)head <= 4 * cap; ++head) {
+                    const int32_t x = queue[head];
+                    const int32_t h = group_of[(size_t)x];
+                    if (h >= 0 && h != gid && (int)members[(size_t)h].size() * 2 > K_fill && (int)members[(size_t)h].size() < K) {
+                        target = h;
+                        radius_of[(size_t)h] = std::max(radius_of[(size_t)h], level[(size_t)x] + radius_of[(size_t)h] / 2);
+                        break;
+                    }
+                    expand(x);
+                }
+                bfs_reset();
+                if (target >= 0) { members[(size_t)target].push_back(r); group_of[(size_t)r] = target; }
+                else keep.push_back(r);
+            }
+            members[(size_t)gid].swap(keep);
         }
-        slots.swap(sorted);
-        for (int64_t i = 0; i < D; ++i) {
-            const int64_t s_old = slot_of[(size_t)i];
-            slot_of[(size_t)i] = new_pos[(size_t)(s_old / K)] * K + s_old % K;
+    }
+    // groups in launch order: as found (neighbours along the grouping curve) or longest-first -- a tree is as deep as
+    // its root is far from the far end of the graph, and a spread-out group waits for its slowest tree
+    std::vector<int32_t> order;
+    for (size_t gid = 0; gid < members.size(); ++gid)
+        if (!members[gid].empty()) order.push_back((int32_t)gid);
+    if (longest_first) {
+        auto score = [&](int32_t gid) {
+            return (g->ecc_h.empty() ? 0 : (int64_t)g->ecc_h[(size_t)seed_of[(size_t)gid]]) + 2 * (int64_t)radius_of[(size_t)gid];
+        };
+        std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return score(x) > score(y); });
+    }
+    slots.assign(order.size() * (size_t)K, -1);
+    for (size_t pos = 0; pos < order.size(); ++pos) {
+        const std::vector<int32_t> &mem = members[(size_t)order[pos]];
+        for (size_t k = 0; k < mem.size(); ++k) {
+            slots[pos * (size_t)K + k] = mem[k];
+            slot_of[(size_t)idx_of[(size_t)mem[k]]] = (int64_t)(pos * (size_t)K + k);
         }
     }
 }
@@ -1418,7 +1501,7 @@ extern "C" int s4_sim_create(s4_graph *g, int64_t T, const int32_t *origin, cons
         CU(cudaMemcpyAsync(vin.p, target_h, (size_t)T * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     }
     if ((rc = sim_group(sim, kin, vin))) return rc;
-    if ((rc = sim_regroup(sim, layout_of(ctx->opt).K))) return rc;
+    if ((rc = sim_regroup(sim, layout_for(g).K))) return rc;
     guard.s = nullptr;
     ++g->refs;
     *out = sim;
@@ -1474,7 +1557,7 @@ extern "C" int s4_sim_create_sampled(s4_graph *g, int64_t T, int64_t n_origins, 
         CU(cudaStreamSynchronize(st));                                   // mr / mt / d_r / d_t go out of scope
     }
     if ((rc = sim_group(sim, kin, vin))) return rc;
-    if ((rc = sim_regroup(sim, layout_of(ctx->opt).K))) return rc;
+    if ((rc = sim_regroup(sim, layout_for(g).K))) return rc;
     guard.s = nullptr;
     ++g->refs;
     *out = sim;
@@ -1691,8 +1774,18 @@ extern "C" int s4_sim_step(s4_sim *sim)
     // ... and with at most four waves of groups in the whole day they are started longest-first (expected depth of the
     // trees + spread of the group), all in one launch per lane-slot, so that the work queue packs the waves
     const bool few_waves = K > 1 && ctx->opt.balance_waves && (sim->D + K_fill - 1) / K_fill <= 4 * (int64_t)std::max(1, L.units());
-    if ((sim->grouped_K != (int)K || sim->grouped_fill != K_fill || sim->grouped_longest_first != few_waves) &&
-        (rc = sim_regroup(sim, (int)K, K_fill, few_waves))) return rc;
+    if (sim->grouped_K != (int)K || sim->grouped_fill0 != K_fill || sim->grouped_longest_first != few_waves) {
+        // the clustering leaves some groups short, so their number is only known afterwards: a handful of groups
+        // beyond whole waves would cost a whole group time -- then the groups take one tree more, and again
+        int fill = K_fill;
+        for (int attempt = 0;; ++attempt) {
+            if ((rc = sim_regroup(sim, (int)K, fill, few_waves))) return rc;
+            const int64_t W = std::max(1, L.units()), Gn = sim->Dp / K, over = Gn % W;
+            if (!few_waves || over == 0 || over > W / 8 || fill >= (int)K || attempt >= 6) break;
+            ++fill;
+        }
+        sim->grouped_fill0 = K_fill;
+    }
     const int64_t D = sim->Dp;                                     // root slots (groups padded to K)
     const int64_t G = D / K;                                       // slots of the distance pool the day needs
     if (D > 0 && (rc = ensure_scratch(g, L, G))) return rc;
@@ -1715,6 +1808,8 @@ extern "C" int s4_sim_step(s4_sim *sim)
     // the day is long enough for the walk of one batch to hide under the SSSP of the next
     if (split) B = std::min(B, std::max<int64_t>(std::max<int64_t>(1, (G + ctx->opt.min_batches - 1) / ctx->opt.min_batches),
                                                   ctx->opt.balance_waves ? 2 * (int64_t)std::max(1, L.units()) : 1));
+    // whole waves per launch where a launch holds several (a partly filled last wave costs a whole group time)
+    if (ctx->opt.balance_waves && B > (int64_t)L.units()) B -= B % (int64_t)L.units();
     const int64_t n_batches = G > 0 ? (G + B - 1) / B : 0;
     g->glog_groups = 0;
     if (ctx->opt.group_log && L.gfn && G > 0) {

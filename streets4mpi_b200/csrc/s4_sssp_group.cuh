@@ -70,9 +70,11 @@ __device__ __forceinline__ void ld_words(const u64 *p, u64 (&x)[TL])
 {
     if constexpr (TL == 1) {
         x[0] = __ldcg(p);
-    } else {
-        static_assert(TL == 2, "one or two words per lane");
+    } else if constexpr (TL == 2) {
         asm volatile("ld.global.cg.v2.u64 {%0,%1}, [%2];" : "=l"(x[0]), "=l"(x[1]) : "l"(p));
+    } else {
+        static_assert(TL == 4, "one, two or four words per lane");
+        asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(x[0]), "=l"(x[1]), "=l"(x[2]), "=l"(x[3]) : "l"(p));   // LDG.E.256
     }
 }
 
@@ -176,8 +178,10 @@ __device__ __forceinline__ u32 subwarp_min4(u32 x0, u32 x1, u32 x2, u32 x3, u32 
     return z;
 }
 
+// CTAs per SM: 1024 threads per SM at 64 registers; with four words per lane a 512-thread CTA takes the SM alone (128
+// registers: the distances of two neighbour rows alone are 16)
 template <int BLOCK, int LP, int TL, int CL = 1>
-__global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024 / BLOCK : 1)) sssp_group_kernel(GroupParams p)
+__global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? (TL >= 4 && BLOCK == 512 ? 1 : 1024 / BLOCK) : 1)) sssp_group_kernel(GroupParams p)
 {
     static_assert(BLOCK % 32 == 0, "whole warps");
     constexpr int RW = LP * TL;           // words per row
@@ -334,33 +338,41 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? 1024
                     }
                     const bool ovf = valid && (a[0].col & kOvfBit) != 0u;
                     u32 vj[kEllWidth];
-                    u64 dv[kEllWidth][TL];
 #pragma unroll
-                    for (int j = 0; j < kEllWidth; ++j) {
-                        vj[j] = a[j].col & ~kOvfBit;
-#pragma unroll
-                        for (int q = 0; q < TL; ++q) dv[j][q] = 0ull;           // nothing improves on 0
-                        // padding slots and self loops point back at u: nothing to relax, no read
-                        if (valid && vj[j] != u) ld_words<TL>(rows + (size_t)vj[j] * RW + t * TL, dv[j]);
-                    }
+                    for (int j = 0; j < kEllWidth; ++j) vj[j] = a[j].col & ~kOvfBit;
                     bool ok[TL];
 #pragma unroll
                     for (int q = 0; q < TL; ++q) ok[q] = !(meta_lane && q == TL - 1) && hi32(my[q]) <= thr_hi;
                     u32 xmin[kEllWidth];
                     u32 bal_imp[kEllWidth], bal_new[kEllWidth], bal_bey[kEllWidth];
+                    // the neighbour rows of STAGE arcs are in flight together: all four with up to two words per lane; with
+                    // four words (rows of 256 bytes, 31 trees) two at a time, or the distances alone would take 32 registers
+                    constexpr int STAGE = TL >= 4 ? 2 : kEllWidth;
 #pragma unroll
-                    for (int j = 0; j < kEllWidth; ++j) {
-                        bool im, beyond;
-                        relax_words<TL>(rows + (size_t)vj[j] * RW + t * TL, my, ok, a[j].w, dv[j], meta_lane, thr_hi, xmin[j], im, beyond);
-                        bal_imp[j] = __ballot_sync(0xffffffffu, im);
-                        bal_bey[j] = __ballot_sync(0xffffffffu, beyond);
-                        // the meta lane holds v's stamp: not yet queued for the coming round?
-                        bal_new[j] = __ballot_sync(0xffffffffu, meta_lane && (u32)dv[j][TL - 1] != rid_next);
+                    for (int s0 = 0; s0 < kEllWidth; s0 += STAGE) {
+                        u64 dv[STAGE][TL];
+#pragma unroll
+                        for (int jj = 0; jj < STAGE; ++jj) {
+#pragma unroll
+                            for (int q = 0; q < TL; ++q) dv[jj][q] = 0ull;       // nothing improves on 0
+                            // padding slots and self loops point back at u: nothing to relax, no read
+                            if (valid && vj[s0 + jj] != u) ld_words<TL>(rows + (size_t)vj[s0 + jj] * RW + t * TL, dv[jj]);
+                        }
+#pragma unroll
+                        for (int jj = 0; jj < STAGE; ++jj) {
+                            const int j = s0 + jj;
+                            bool im, beyond;
+                            relax_words<TL>(rows + (size_t)vj[j] * RW + t * TL, my, ok, a[j].w, dv[jj], meta_lane, thr_hi, xmin[j], im, beyond);
+                            bal_imp[j] = __ballot_sync(0xffffffffu, im);
+                            bal_bey[j] = __ballot_sync(0xffffffffu, beyond);
+                            // the meta lane holds v's stamp: not yet queued for the coming round?
+                            bal_new[j] = __ballot_sync(0xffffffffu, meta_lane && (u32)dv[jj][TL - 1] != rid_next);
+                        }
                     }
                     // sub-warp minimum of the (updated) distances of every head: lane t gets slot j(t)
                     const u32 zmin = subwarp_min4<LP>(xmin[0], xmin[1], xmin[2], xmin[3], t);
-                    const u32 j = LP == 8 ? t >> 1 : t;
                     const bool pusher = LP == 8 ? (t & 1u) == 0u : true;
+                    const u32 j = LP == 8 ? t >> 1 : t;
                     const bool any_imp = ((sel4(j, bal_imp[0], bal_imp[1], bal_imp[2], bal_imp[3]) >> sub_shift) & LPMASK) != 0u;
                     const bool any_bey = ((sel4(j, bal_bey[0], bal_bey[1], bal_bey[2], bal_bey[3]) >> sub_shift) & LPMASK) != 0u;
                     const bool fresh = ((sel4(j, bal_new[0], bal_new[1], bal_new[2], bal_new[3]) >> sub_shift) & LPMASK) != 0u;

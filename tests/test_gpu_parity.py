@@ -152,7 +152,10 @@ def test_road_construction_golden(dev, phys):
                                   dict(early_advance=64, block_threads=32, near_smem_entries=32),
                                   # thread-block clusters sharing one group (the large-graph configuration)
                                   dict(cluster=2, block_threads=512), dict(cluster=8, block_threads=1024),
-                                  dict(cluster=4, block_threads=1024, delta_factor=0.5, early_advance=64)])
+                                  dict(cluster=4, block_threads=1024, delta_factor=0.5, early_advance=64),
+                                  # other group widths: 7 and 31 trees per group (rows of 64 / 256 bytes), 3 per group on 4 lanes
+                                  dict(group_words=1), dict(group_words=2), dict(group_words=4), dict(group_words=4, block_threads=512),
+                                  dict(group_lanes=4, group_words=1)])
 @pytest.mark.parametrize("ranked", [False, True])
 def test_sssp_dist_and_pred_vs_oracle(dev, shape, opts, ranked):
     """Single trees: distances bit-equal to Dijkstra, predecessors equal under the canonical rule;
@@ -416,6 +419,42 @@ def test_queue_overflow_falls_back_to_sweeps(dev, phys, preread):
         d0, p0, _ = ctwin.sssp(ctwin.Csr(V, arr["u"], arr["v"]), w, 5)
         assert np.array_equal(dist.view(np.uint64), d0.view(np.uint64))
         assert np.array_equal(pred, p0)
+        g.close()
+    finally:
+        for k, val in old.items():
+            dev.set_option(k, val)
+
+
+@pytest.mark.parametrize("words,block", [(1, 0), (2, 0), (4, 0), (4, 512), (4, 128)])
+def test_group_widths_day(dev, phys, words, block):
+    """7 and 31 trees per group (rows of 64 and 256 bytes; 31 trees take the neighbour rows two at a time): a day of
+    6 k trips to 1500 goals equals the oracle's, on two days with the congestion feedback between them."""
+    from oracle import ctwin
+    from streets4mpi_b200 import engine, synth
+    arr = synth.grid_arrays(80, 100, seed=23)
+    V = len(arr["node_ids"])
+    rng = np.random.default_rng(18)
+    o = rng.integers(0, V, 6000).astype(np.int32)
+    gl = rng.choice(V, 1500, replace=False)[rng.integers(0, 1500, 6000)].astype(np.int32)
+    keys = ("group_words", "block_threads", "root_mode")
+    old = {k: dev.get_option(k) for k in keys}
+    try:
+        dev.set_option("group_words", words)
+        dev.set_option("block_threads", block)
+        dev.set_option("root_mode", 1)
+        g = engine.DeviceGraph(dev, V, arr["u"], arr["v"], arr["length"], arr["max_speed"])
+        sim = engine.DeviceSim(g, o, gl, 0.3, phys)
+        csr = ctwin.Csr(V, arr["u"], arr["v"])
+        prev = np.zeros(len(arr["u"]), dtype=np.uint32)
+        for _ in range(2):
+            sim.step()
+            want, cnt = ctwin.day(csr, ctwin.weights(arr["length"], arr["max_speed"], prev, 0.3), gl, o, nthreads=4)
+            assert np.array_equal(sim.get_load(), want)
+            sim.commit_total()
+            prev = want
+        c = sim.counters()
+        assert c["trips_routed"] == 12000 and c["trips_stuck"] == 0
+        sim.close()
         g.close()
     finally:
         for k, val in old.items():
