@@ -499,6 +499,16 @@ def gpu_arm(args):
     barrier()
     cs = sim.counters()
     dev.set_option("lanes", 2)
+    # what every GPU did (rank 0 prints it): a day ends with an all-reduce, so the slowest GPU sets the pace
+    slots_r, k_r = sim._sim.root_slots()
+    mine = {"rank": rank, "trees": int(sim._sim.n_roots), "groups": int(len(slots_r) // max(1, k_r)), "trees_per_group_slots": int(k_r),
+            "ms_timed_region_per_day": ms / args.steps, "ms_sssp_serial_day": cs["ms_sssp"], "ms_walk_serial_day": cs["ms_walk"],
+            "sssp_launches_serial_day": int(cs["sssp_launches"]), "fallback_sweeps": int(c["fallback_sweeps"]),
+            "trips_stuck": int(c["trips_stuck"])}
+    rank_report = [mine]
+    if world > 1:
+        rank_report = [None] * world
+        dist.all_gather_object(rank_report, mine)
 
     # ---- secondary measurements: every number the design notes quote gets a driver-run twin (a few seconds each)
     peak_gbs, _ = measured_peak()
@@ -648,6 +658,7 @@ def gpu_arm(args):
                     "api": "reference driver protocol (streets4mpi.py:93-100): Simulation.step(), array('I') "
                            "traffic_load read + assign, merge_arrays into cumulative_traffic_load; wall clock"},
             "gpu_launches": int(launches),
+            "per_rank": rank_report,
             "per_day_ms_rank0": [round(x, 3) for x in per_day_ms] if args.per_day else None,
             "road_construction": {"events_in_timed_region": adapt_events,
                                   "ms_per_event_rank0": c["ms_adapt"] / adapt_events if adapt_events else None,

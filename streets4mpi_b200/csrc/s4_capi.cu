@@ -5,6 +5,7 @@
 #include "../../include/s4mpi.h"
 #include "s4_kernels.cuh"
 #include "s4_sssp_group.cuh"
+#include "s4_walk_codes.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -76,6 +77,9 @@ struct Options {
     double lag_factor = 1.0;        // source-batched kernel: hold a node back by this multiple of the root-to-root distance
     int group_log = 0;              // diagnostics: keep per-group cycles / rounds / entries of the last day (s4_graph_group_log)
     int min_batches = 4;            // a day is cut into at least this many (SSSP launch -> walk) batches when lanes = 2
+    int walk_codes = 2;             // 1: resolve every (node, tree) predecessor once (2-bit codes in the rows' meta words), then
+                                    // one-lane walks; 0: walks derive predecessors on the fly; 2 = codes when the day has at
+                                    // least 150 trips per tree (the streaming pass costs about as much as 100 trips per tree)
     int l2_persist = 0;             // 1: keep the fixed-stride arc rows (64 B per node, read by every expansion and every
                                     // hop) resident in L2 with an access-policy window on both lanes' streams
     int balance_waves = 1;          // fewer trees per group when that fills the last wave of a launch (few groups per GPU)
@@ -338,7 +342,7 @@ static void option_slot(Options &o, const char *key, int *kind, void **raw)
         {"group_words", 1, &o.group_words},         {"lag_factor", 0, &o.lag_factor},
         {"min_batches", 1, &o.min_batches},         {"group_log", 1, &o.group_log},
         {"cluster", 1, &o.cluster},                 {"balance_waves", 1, &o.balance_waves},
-        {"l2_persist", 1, &o.l2_persist},
+        {"l2_persist", 1, &o.l2_persist},           {"walk_codes", 1, &o.walk_codes},
     };
     for (auto &it : items)
         if (strcmp(it.k, key) == 0) { *kind = it.kind; *raw = it.p; return; }
@@ -370,7 +374,8 @@ extern "C" int s4_ctx_set_option(s4_ctx *ctx, const char *key, double value)
               (t.group_words == 0 || t.group_words == 1 || t.group_words == 2 || (t.group_words == 4 && t.group_lanes != 4)) &&
               t.lag_factor >= 0.0 && t.lag_factor <= 64.0 && t.min_batches >= 1 && t.min_batches <= 64 &&
               (t.cluster == 0 || t.cluster == 1 || t.cluster == 2 || t.cluster == 4 || t.cluster == 8) &&
-              (t.l2_persist == 0 || t.l2_persist == 1) && (t.balance_waves == 0 || t.balance_waves == 1);
+              (t.l2_persist == 0 || t.l2_persist == 1) && (t.balance_waves == 0 || t.balance_waves == 1) &&
+              t.walk_codes >= 0 && t.walk_codes <= 2;
     if (!ok) return fail(S4_ERR_ARG, "option '%s': value %g out of range", key, value);
     ctx->opt = trial;
     return S4_OK;
@@ -871,7 +876,7 @@ static int scratch_budget(s4_graph *g, double *pool_budget, double *ws_budget)
 // Trees per group.  A group of 31 (four words per lane, rows of 256 bytes) costs 1.65x the time of a group of 15 on cfg3:
 // 20 % less SM time per tree.  It needs twice the pool per slot, so it is taken when both lanes can still hold a slot
 // per SM; larger graphs keep 15 (and, beyond that, clusters).  Decided once per graph and option setting.
-static int group_words_for(s4_graph *g)
+static int group_words_for(s4_graph *g, int64_t D)
 {
     const Options &o = g->ctx->opt;
     if (o.group_lanes == 0) return 1;
@@ -886,15 +891,18 @@ static int group_words_for(s4_graph *g)
             if (slots >= 2.0 * (double)g->ctx->prop.multiProcessorCount) g->auto_words = 4;
         }
     }
+    // ... and the day must have at least 2.5 waves of such groups: with fewer (several GPUs sharing a day) the smaller
+    // groups pack the SMs better (cfg3 on 8 GPUs: 96 ms against 115 ms per day and GPU)
+    if (g->auto_words == 4 && (D + 30) / 31 * 2 < 5 * (int64_t)g->ctx->prop.multiProcessorCount) return 2;
     return g->auto_words;
 }
-static Layout layout_for(s4_graph *g) { return layout_of(g->ctx->opt, group_words_for(g)); }
+static Layout layout_for(s4_graph *g, int64_t D) { return layout_of(g->ctx->opt, group_words_for(g, D)); }
 
-static int plan_sssp(s4_graph *g, SsspLaunch *L)
+static int plan_sssp(s4_graph *g, SsspLaunch *L, int64_t D)
 {
     const Options &o = g->ctx->opt;
-    L->lay = layout_for(g);
-    const int words = group_words_for(g);
+    L->lay = layout_for(g, D);
+    const int words = group_words_for(g, D);
     const bool grouped = o.group_lanes > 0;
     // CTA width from the graph's wave width (graph upload): a tree keeps about `auto_block` nodes in flight per
     // relaxation round; the source-batched kernel spends group_lanes lanes on every node it expands
@@ -1100,6 +1108,32 @@ static int launch_pred(s4_graph *g, const Arc *arcs, const u64 *dist, u32 stride
     return S4_OK;
 }
 
+// predecessor codes for the group slots of a batch, then one-lane walks; slow nodes go to walk_slow_kernel
+static int launch_walk_codes(s4_graph *g, const WalkParams &p, int n_groups, int words, cudaStream_t st)
+{
+    CodeParams cp;
+    cp.ellw = p.ellw;
+    cp.pool = const_cast<u64 *>(p.dist_pool);
+    cp.slot_stride = p.slot_stride;
+    cp.n_groups = n_groups;
+    cp.V = p.V;
+    const int sms = g->ctx->prop.multiProcessorCount;
+    const int64_t subwarps = (int64_t)n_groups * (int64_t)p.V;
+    const int code_grid = (int)std::max<int64_t>(1, std::min<int64_t>((subwarps * 8 + 255) / 256, (int64_t)sms * 8));
+    switch (words) {
+        case 1: pred_code_kernel<1><<<code_grid, 256, 0, st>>>(cp); break;
+        case 2: pred_code_kernel<2><<<code_grid, 256, 0, st>>>(cp); break;
+        default: pred_code_kernel<4><<<code_grid, 256, 0, st>>>(cp); break;
+    }
+    CU(cudaGetLastError());
+    const int grid = grid_for(p.t1 - p.t0, 256, g->ctx);
+    walk_code_kernel<<<grid, 256, 0, st>>>(p);
+    CU(cudaGetLastError());
+    walk_slow_kernel<8><<<grid_for((p.t1 - p.t0) * 8, 256, g->ctx), 256, 0, st>>>(p);      // ties / plateaus / wide nodes: may be many
+    CU(cudaGetLastError());
+    return S4_OK;
+}
+
 static int launch_walk(s4_graph *g, const WalkParams &p, cudaStream_t st)
 {
     const int tile = g->ctx->opt.walk_tile ? g->ctx->opt.walk_tile : g->auto_walk_tile;
@@ -1126,7 +1160,7 @@ extern "C" int s4_graph_sssp(s4_graph *g, const double *w_street, int32_t origin
     for (int64_t s = 0; s < g->S; ++s)
         if (!(w_street[s] >= 0.0)) return fail(S4_ERR_ARG, "street %lld: weight must be >= 0", (long long)s);
     SsspLaunch L;
-    int rc = plan_sssp(g, &L);
+    int rc = plan_sssp(g, &L, 1);
     if (rc) return rc;
     rc = ensure_scratch(g, L, 1);
     if (rc) return rc;
@@ -1421,6 +1455,7 @@ static int sim_regroup(s4_sim *sim, int K, int K_fill = 0, bool longest_first = 
 {
     if (K_fill <= 0 || K_fill > K) K_fill = K;
     sim->grouped_fill = K_fill;
+    sim->grouped_fill0 = K_fill;
     sim->grouped_longest_first = longest_first;
     s4_graph *g = sim->g;
     s4_ctx *ctx = g->ctx;
@@ -1501,7 +1536,7 @@ extern "C" int s4_sim_create(s4_graph *g, int64_t T, const int32_t *origin, cons
         CU(cudaMemcpyAsync(vin.p, target_h, (size_t)T * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     }
     if ((rc = sim_group(sim, kin, vin))) return rc;
-    if ((rc = sim_regroup(sim, layout_for(g).K))) return rc;
+    if ((rc = sim_regroup(sim, layout_for(g, sim->D).K))) return rc;
     guard.s = nullptr;
     ++g->refs;
     *out = sim;
@@ -1557,7 +1592,7 @@ extern "C" int s4_sim_create_sampled(s4_graph *g, int64_t T, int64_t n_origins, 
         CU(cudaStreamSynchronize(st));                                   // mr / mt / d_r / d_t go out of scope
     }
     if ((rc = sim_group(sim, kin, vin))) return rc;
-    if ((rc = sim_regroup(sim, layout_for(g).K))) return rc;
+    if ((rc = sim_regroup(sim, layout_for(g, sim->D).K))) return rc;
     guard.s = nullptr;
     ++g->refs;
     *out = sim;
@@ -1666,25 +1701,34 @@ static int ev_end(std::vector<EvPair> &v, size_t &used, cudaStream_t st)
     ++used;
     return S4_OK;
 }
-static int ev_harvest(std::vector<EvPair> &v, size_t &used, double *acc)
+// wait = false: only the pairs that have completed (a prefix; the rest moves to the front and is harvested later), so
+// that s4_sim_step never waits for the previous day: the host queues day N+1 while the GPU still runs day N
+static int ev_harvest(std::vector<EvPair> &v, size_t &used, double *acc, bool wait)
 {
-    for (size_t i = 0; i < used; ++i) {
-        CU(cudaEventSynchronize(v[i].b));
+    size_t done = 0;
+    for (; done < used; ++done) {
+        if (wait) CU(cudaEventSynchronize(v[done].b));
+        else {
+            cudaError_t q = cudaEventQuery(v[done].b);
+            if (q == cudaErrorNotReady) break;
+            CU(q);
+        }
         float ms = 0.f;
-        CU(cudaEventElapsedTime(&ms, v[i].a, v[i].b));
+        CU(cudaEventElapsedTime(&ms, v[done].a, v[done].b));
         *acc += (double)ms;
     }
-    used = 0;
+    std::rotate(v.begin(), v.begin() + (ptrdiff_t)done, v.begin() + (ptrdiff_t)used);
+    used -= done;
     return S4_OK;
 }
-static int harvest_all(s4_sim *sim)
+static int harvest_all(s4_sim *sim, bool wait = true)
 {
     int rc;
-    if ((rc = ev_harvest(sim->ev_w, sim->used_w, &sim->acc.ms_weights))) return rc;
-    if ((rc = ev_harvest(sim->ev_sssp, sim->used_sssp, &sim->acc.ms_sssp))) return rc;
-    if ((rc = ev_harvest(sim->ev_walk, sim->used_walk, &sim->acc.ms_walk))) return rc;
-    if ((rc = ev_harvest(sim->ev_adapt, sim->used_adapt, &sim->acc.ms_adapt))) return rc;
-    if ((rc = ev_harvest(sim->ev_step, sim->used_step, &sim->acc.ms_step_total))) return rc;
+    if ((rc = ev_harvest(sim->ev_w, sim->used_w, &sim->acc.ms_weights, wait))) return rc;
+    if ((rc = ev_harvest(sim->ev_sssp, sim->used_sssp, &sim->acc.ms_sssp, wait))) return rc;
+    if ((rc = ev_harvest(sim->ev_walk, sim->used_walk, &sim->acc.ms_walk, wait))) return rc;
+    if ((rc = ev_harvest(sim->ev_adapt, sim->used_adapt, &sim->acc.ms_adapt, wait))) return rc;
+    if ((rc = ev_harvest(sim->ev_step, sim->used_step, &sim->acc.ms_step_total, wait))) return rc;
     return S4_OK;
 }
 
@@ -1756,39 +1800,40 @@ extern "C" int s4_sim_step(s4_sim *sim)
     s4_ctx *ctx = g->ctx;
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    int rc = harvest_all(sim);          // events of the previous day (already complete in practice)
+    int rc = harvest_all(sim, false);   // the timing events of earlier days that have completed; never waits
     if (rc) return rc;
     SsspLaunch L;
-    if ((rc = plan_sssp(g, &L))) return rc;
+    if ((rc = plan_sssp(g, &L, sim->D))) return rc;
     const int64_t K = L.lay.K;
     // Trees per group.  A launch runs L.units() groups at a time; when the day has only a few waves of groups (several
     // GPUs sharing a day), a partly filled last wave costs a whole group time: then the groups take fewer trees, so
     // that their number fills whole waves (4 % head room: the greedy clustering leaves some groups short).
     int K_fill = (int)K;
+    int64_t waves_wanted = 0;                                      // 0: many waves, their number does not matter
     if (K > 1 && sim->D > 0 && ctx->opt.balance_waves) {
         const int64_t W = std::max(1, L.units());
         const int64_t G0 = (sim->D + K - 1) / K, waves = (G0 + W - 1) / W;
         const double target = 0.96 * (double)(waves * W);
         K_fill = (int)std::min<int64_t>(K, std::max<int64_t>(1, (int64_t)std::ceil((double)sim->D / std::max(1.0, target))));
+        if (waves <= 4) waves_wanted = waves;
     }
     // ... and with at most four waves of groups in the whole day they are started longest-first (expected depth of the
     // trees + spread of the group), all in one launch per lane-slot, so that the work queue packs the waves
-    const bool few_waves = K > 1 && ctx->opt.balance_waves && (sim->D + K_fill - 1) / K_fill <= 4 * (int64_t)std::max(1, L.units());
+    const bool few_waves = waves_wanted > 0;
     if (sim->grouped_K != (int)K || sim->grouped_fill0 != K_fill || sim->grouped_longest_first != few_waves) {
-        // the clustering leaves some groups short, so their number is only known afterwards: a handful of groups
-        // beyond whole waves would cost a whole group time -- then the groups take one tree more, and again
+        // the clustering leaves some groups short, so their number is only known afterwards: groups beyond the
+        // intended waves would cost a whole group time -- then every group takes one tree more, and again
         int fill = K_fill;
         for (int attempt = 0;; ++attempt) {
             if ((rc = sim_regroup(sim, (int)K, fill, few_waves))) return rc;
-            const int64_t W = std::max(1, L.units()), Gn = sim->Dp / K, over = Gn % W;
-            if (!few_waves || over == 0 || over > W / 8 || fill >= (int)K || attempt >= 6) break;
+            if (!few_waves || sim->Dp / K <= waves_wanted * (int64_t)std::max(1, L.units()) || fill >= (int)K || attempt >= 12) break;
             ++fill;
         }
         sim->grouped_fill0 = K_fill;
     }
     const int64_t D = sim->Dp;                                     // root slots (groups padded to K)
     const int64_t G = D / K;                                       // slots of the distance pool the day needs
-    if (D > 0 && (rc = ensure_scratch(g, L, G))) return rc;
+    if (D > 0 && (rc = ensure_scratch(g, L, G + (G & 1)))) return rc;   // an even number of slots: two lanes of ceil(G / 2)
 
     if ((rc = ev_begin(sim->ev_step, sim->used_step, st))) return rc;
     // ---- K1 (simulation.py:53-65) + reset of today's counters (:68)
@@ -1802,7 +1847,8 @@ extern "C" int s4_sim_step(s4_sim *sim)
     // while it drains its last trees, and the walk (a latency-bound pointer chase) hides under the other lane's
     // SSSP.  A day is cut into at least `min_batches` batches even when all its trees would fit the pool at once.
     const int64_t slots = std::max<int64_t>(1, g->pool_slots);
-    const bool split = ctx->opt.lanes >= 2 && slots >= 2 && G >= 2;
+    // a day of a single wave of groups that all fit in the pool is one launch (nothing for a second lane to overlap with)
+    const bool split = ctx->opt.lanes >= 2 && slots >= 2 && G >= 2 && !(waves_wanted == 1 && slots >= G);
     int64_t B = split ? slots / 2 : slots;                         // slots per launch
     // a launch should hold at least two waves of groups (the work queue then packs them); more launches only when
     // the day is long enough for the walk of one batch to hide under the SSSP of the next
@@ -1865,6 +1911,7 @@ extern "C" int s4_sim_step(s4_sim *sim)
         wp.row_ptr = g->row_ptr.p;
         wp.arcs = sim->arcs.p;
         wp.ellw = ctx->opt.walk_ell ? sim->ellw.p : nullptr;
+        wp.ell_cs = g->ell_cs.p;
         wp.orig = g->orig.p;
         wp.slot_stride = sw;
         wp.group = (u32)K;
@@ -1884,7 +1931,14 @@ extern "C" int s4_sim_step(s4_sim *sim)
         wp.deferred = sim->deferred.p + wp.t0;
         wp.deferred_count = sim->deferred_counts.p + bi;
         if ((rc = ev_begin(sim->ev_walk, sim->used_walk, ls))) return rc;
-        if ((rc = launch_walk(g, wp, ls))) return rc;
+        // trip-heavy days: every (node, tree) predecessor is resolved once, the walks then take one lane and one
+        // dependent access per hop
+        const bool codes = L.gfn && ctx->opt.group_lanes == 8 && wp.ellw &&
+                           (ctx->opt.walk_codes == 1 || (ctx->opt.walk_codes == 2 && sim->T >= 150 * std::max<int64_t>(1, sim->D)));
+        if (codes) rc = launch_walk_codes(g, wp, (int)((r1 - r0 + K - 1) / K), L.lay.RW / 8, ls);
+        else rc = launch_walk(g, wp, ls);
+        if (rc) return rc;
+        if (codes) ++sim->acc.kernel_launches;
         if ((rc = ev_end(sim->ev_walk, sim->used_walk, ls))) return rc;
         sim->acc.kernel_launches += 2;
     }

@@ -854,6 +854,7 @@ struct WalkParams {
     const u32 *row_ptr;
     const Arc *arcs;
     const Arc *ellw;            // fixed-stride rows with street indices (nullptr: CSR only)
+    const uint2 *ell_cs;        // static fixed-stride rows {head | overflow flag, street | reverse slot << 29} (walk_code_kernel)
     const u32 *orig;            // device number -> caller's node id (nullptr = identity)
     const u64 *dist_pool;       // first slot of this batch
     size_t slot_stride;         // words per slot (a slot holds the rows of `group` trees)

@@ -128,8 +128,6 @@ class Simulation(object):
     def step(self):
         self.step_counter += 1
         self.log_callback("Preparing edges...")
-        if self.step_counter > 1:
-            self._check_stuck()                  # yesterday's walks (the library waits for that day here anyway)
         self._push_host_state()
         self._sim.step()                         # K1 -> K2 -> K3, asynchronous
         self._host_load = None
@@ -144,6 +142,7 @@ class Simulation(object):
         distributed.exchange([self] + list(virtual_ranks or []), group)
 
     def road_construction(self):
+        self._check_stuck()                      # a synchronising call anyway (the new limits are read back)
         self._push_host_state()
         mask = self.street_network.flat().adaptable if device_settings.get("orientation_aliasing", True) else None
         self._sim.road_construction(mask)

@@ -425,6 +425,62 @@ def test_queue_overflow_falls_back_to_sweeps(dev, phys, preread):
             dev.set_option(k, val)
 
 
+@pytest.mark.parametrize("words", [1, 2, 4])
+@pytest.mark.parametrize("case", ["unique", "ties", "plateaus", "wide_nodes"])
+def test_walk_with_predecessor_codes_matches_oracle(dev, phys, words, case):
+    """walk_codes=1: a streaming pass writes the canonical predecessor of every (node, tree) as a 2-bit arc-slot code, one
+    lane per trip follows the codes, and ties / zero-weight plateaus / nodes with more than four arcs fall back to the
+    full rule from that node on.  Loads and counters must equal the oracle's on unique shortest paths, on a grid of equal
+    lengths (nearly every node tied), with 25 % zero-length streets, and on a planar graph with wide nodes."""
+    from oracle import ctwin
+    from streets4mpi_b200 import engine, synth
+    rng = np.random.default_rng(31)
+    if case == "wide_nodes":
+        arr = synth.planar_arrays(4000, seed=6)
+        V, u, v, L, ms = len(arr["node_ids"]), arr["u"], arr["v"], arr["length"], arr["max_speed"]
+    else:
+        rows, cols = 40, 50
+        V = rows * cols
+        idx = np.arange(V).reshape(rows, cols)
+        u = np.concatenate([idx[:, :-1].ravel(), idx[:-1, :].ravel()]).astype(np.int32)
+        v = np.concatenate([idx[:, 1:].ravel(), idx[1:, :].ravel()]).astype(np.int32)
+        S = len(u)
+        ms = np.full(S, 50, dtype=np.int32)
+        if case == "unique":
+            L = rng.uniform(20.0, 400.0, S)
+        elif case == "ties":
+            L = np.full(S, 100.0)
+        else:
+            L = np.where(rng.random(S) < 0.25, 0.0, rng.integers(1, 4, S) * 50.0)
+    o = rng.integers(0, V, 5000).astype(np.int32)
+    gl = rng.choice(V, 300, replace=False)[rng.integers(0, 300, 5000)].astype(np.int32)
+    keys = ("group_words", "walk_codes", "root_mode")
+    old = {k: dev.get_option(k) for k in keys}
+    try:
+        dev.set_option("group_words", words)
+        dev.set_option("walk_codes", 1)
+        dev.set_option("root_mode", 1)
+        g = engine.DeviceGraph(dev, V, u, v, L, ms, node_rank=rng.permutation(V).astype(np.int32))
+        sim = engine.DeviceSim(g, o, gl, 0.4, phys)
+        csr = ctwin.Csr(V, u, v)
+        prev = np.zeros(len(u), dtype=np.uint32)
+        hops = stuck = unreach = 0
+        for _ in range(2):
+            sim.step()
+            want, cnt = ctwin.day(csr, ctwin.weights(L, ms, prev, 0.4), gl, o, nthreads=4)
+            assert np.array_equal(sim.get_load(), want)
+            hops, stuck, unreach = hops + cnt["hops"], stuck + cnt["stuck"], unreach + cnt["unreachable"]
+            sim.commit_total()
+            prev = want
+        c = sim.counters()
+        assert (c["hops"], c["trips_stuck"], c["trips_unreachable"], c["trips_routed"]) == (hops, stuck, unreach, 10000)
+        sim.close()
+        g.close()
+    finally:
+        for k, val in old.items():
+            dev.set_option(k, val)
+
+
 @pytest.mark.parametrize("words,block", [(1, 0), (2, 0), (4, 0), (4, 512), (4, 128)])
 def test_group_widths_day(dev, phys, words, block):
     """7 and 31 trees per group (rows of 64 and 256 bytes; 31 trees take the neighbour rows two at a time): a day of
