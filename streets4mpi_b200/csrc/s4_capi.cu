@@ -226,6 +226,9 @@ struct s4_sim {
     std::vector<int64_t> h_root_off;   // Dp+1
     int64_t alg_arcs_per_day = 0, alg_nodes_per_day = 0;
     DevBuf<u32> load, cum;
+    u64 *hops_host = nullptr;      // pinned: the device's hop counter as of the end of the last completed day (heuristics only)
+    u64 hops_seen = 0;             // ... and what it was a day earlier
+    double hops_per_day = 0.0;     // hops walked on the last day whose counter has arrived
     DevBuf<uint2> deferred;        // T: trips the hot walk kernel hands to the slow one (zero-weight plateaus)
     DevBuf<u32> deferred_counts;   // one per batch of the day
     bool has_cum = false;
@@ -1669,6 +1672,7 @@ extern "C" int s4_sim_free(s4_sim *sim)
     free_events(sim->ev_walk);
     free_events(sim->ev_adapt);
     free_events(sim->ev_step);
+    if (sim->hops_host) cudaFreeHost(sim->hops_host);
     s4_graph *g = sim->g;
     delete sim;
     graph_unref(g);
@@ -1895,6 +1899,20 @@ extern "C" int s4_sim_step(s4_sim *sim)
         CU(cudaEventRecord(ctx->sssp_done[0], st));
         CU(cudaStreamWaitEvent(ctx->walk_stream, ctx->sssp_done[0], 0));
     }
+    // predecessor codes pay when the walks are long against the streaming pass over V x trees words: measured on cfg3 the
+    // pass costs what 0.1 * V * D hops cost the eight-lane walk.  Hops of the last day whose counter has arrived;
+    // before that, 150 trips per tree (700-hop trips on cfg3).
+    if (!sim->hops_host) {
+        CU(cudaHostAlloc((void **)&sim->hops_host, sizeof(u64), cudaHostAllocDefault));
+        *sim->hops_host = 0;
+    }
+    {
+        const u64 now = *(volatile u64 *)sim->hops_host;
+        if (now > sim->hops_seen) { sim->hops_per_day = (double)(now - sim->hops_seen); sim->hops_seen = now; }
+        else if (now < sim->hops_seen) { sim->hops_seen = now; }                    // counters were reset
+    }
+    const bool codes_pay = sim->hops_per_day > 0.0 ? sim->hops_per_day >= 0.1 * (double)g->V * (double)std::max<int64_t>(1, sim->D)
+                                                   : sim->T >= 150 * std::max<int64_t>(1, sim->D);
     const size_t sw = slot_words(g, L.lay);
     for (int64_t bi = 0; bi < n_batches; ++bi) {
         const int64_t r0 = bi * B * K, r1 = std::min(D, r0 + B * K);
@@ -1933,8 +1951,7 @@ extern "C" int s4_sim_step(s4_sim *sim)
         if ((rc = ev_begin(sim->ev_walk, sim->used_walk, ls))) return rc;
         // trip-heavy days: every (node, tree) predecessor is resolved once, the walks then take one lane and one
         // dependent access per hop
-        const bool codes = L.gfn && ctx->opt.group_lanes == 8 && wp.ellw &&
-                           (ctx->opt.walk_codes == 1 || (ctx->opt.walk_codes == 2 && sim->T >= 150 * std::max<int64_t>(1, sim->D)));
+        const bool codes = L.gfn && ctx->opt.group_lanes == 8 && wp.ellw && (ctx->opt.walk_codes == 1 || (ctx->opt.walk_codes == 2 && codes_pay));
         if (codes) rc = launch_walk_codes(g, wp, (int)((r1 - r0 + K - 1) / K), L.lay.RW / 8, ls);
         else rc = launch_walk(g, wp, ls);
         if (rc) return rc;
@@ -1946,6 +1963,7 @@ extern "C" int s4_sim_step(s4_sim *sim)
         CU(cudaEventRecord(ctx->walk_done[1], ctx->walk_stream));
         CU(cudaStreamWaitEvent(st, ctx->walk_done[1], 0));
     }
+    CU(cudaMemcpyAsync(sim->hops_host, sim->counters.p + C_HOPS, sizeof(u64), cudaMemcpyDeviceToHost, st));   // for tomorrow's choice
     if ((rc = ev_end(sim->ev_step, sim->used_step, st))) return rc;
     sim->acc.days += 1;
     sim->acc.sssp_instances += (uint64_t)sim->D;

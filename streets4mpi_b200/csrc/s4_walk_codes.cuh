@@ -13,8 +13,9 @@
 //                    candidates (tie: the rule needs ids), sits on a zero-weight plateau, or the node has more arcs
 //                    than the fixed-stride row holds.  Same lane layout and coalesced row accesses as the SSSP expansion.
 // walk_code_kernel   ONE lane per trip and one dependent stage per hop: meta word and arc row are fetched together, the
-//                    code selects the arc.  At a slow node the trip is handed to walk_slow_kernel (the full rule, from
-//                    that node on), so the result is the canonical one bit for bit.
+//                    code selects the arc.  At a slow node the lane applies the rule itself over the CSR row (ties, wide
+//                    nodes); only zero-weight plateaus are handed to walk_slow_kernel (the bounded search, from that node
+//                    on), so the result is the canonical one bit for bit.
 #pragma once
 
 #include "s4_sssp_group.cuh"
@@ -122,16 +123,40 @@ __global__ void __launch_bounds__(256) walk_code_kernel(WalkParams p)
         u32 h0, s0, h1, s1, h2, s2, h3, s3;
         asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                      : "=r"(h0), "=r"(s0), "=r"(h1), "=r"(s1), "=r"(h2), "=r"(s2), "=r"(h3), "=r"(s3) : "l"(p.ell_cs + (size_t)cur * kEllWidth));
+        u32 nxt, street;
         if (meta & kSlowBit) {
-            // tie, plateau or a node with more arcs: the full rule takes over from here (walk_slow_kernel)
-            const u32 slot = atomicAdd(p.deferred_count, 1u);
-            p.deferred[slot] = make_uint2(t_rel, cur);
-            active = false;
-            continue;
+            // a tie in some tree of the group or a node with more arcs than the row holds: this lane applies the rule
+            // itself over the node's CSR row -- smallest (id, street) among the strictly closer candidates
+            const u64 *dist = rows + (shift >> 1);
+            const u64 dv = ld_dist(dist + (size_t)cur * RW);
+            u64 best = ~0ull;
+            u32 best_col = 0u, n_equal = 0u;
+            for (u32 e = __ldg(p.row_ptr + cur), re = __ldg(p.row_ptr + cur + 1); e < re; ++e) {
+                const Arc a = ld_arc(p.arcs + e);
+                if (a.col == cur) continue;
+                const u64 du = ld_dist(dist + (size_t)a.col * RW);
+                if (du >= kInfBits || (u64)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)du), a.w)) != dv) continue;
+                if (du < dv) {
+                    const u64 key = ((u64)(p.orig ? __ldg(p.orig + a.col) : a.col) << 32) | a.street;
+                    if (key < best) { best = key; best_col = a.col; }
+                } else ++n_equal;
+            }
+            if (best == ~0ull) {
+                if (n_equal) {
+                    // a zero-weight plateau: the bounded search of walk_slow_kernel takes over from here
+                    const u32 slot = atomicAdd(p.deferred_count, 1u);
+                    p.deferred[slot] = make_uint2(t_rel, cur);
+                } else ++c_stuck;
+                active = false;
+                continue;
+            }
+            nxt = best_col;
+            street = (u32)best;
+        } else {
+            const u32 j = (u32)(meta >> shift) & 3u;
+            nxt = sel4(j, h0, h1, h2, h3) & ~kOvfBit;
+            street = sel4(j, s0, s1, s2, s3) & 0x1FFFFFFFu;
         }
-        const u32 j = (u32)(meta >> shift) & 3u;
-        const u32 nxt = sel4(j, h0, h1, h2, h3) & ~kOvfBit;
-        const u32 street = sel4(j, s0, s1, s2, s3) & 0x1FFFFFFFu;
         if (nxt == cur || ++guard > p.V) { ++c_stuck; active = false; continue; }      // never with a converged slot
         atomicAdd(p.load + street, p.volume);                                          // :86-88
         ++c_hops;
