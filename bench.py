@@ -9,8 +9,9 @@ A step is one simulated day: K1 weights -> K2 one shortest-path tree per root ->
 trip -> exchange (NCCL all-reduce of the uint32 load + cumulative merge).  Workload (config.workload):
 BASELINE.json configs[2], the synthetic 1024x1024 grid (V=1,048,576 S=2,095,104 A=4,190,208), 1M
 trips/day, goals = seeded 2 % node sample.  Default --scaling strong: ONE virtual rank (one trip list, one jam
-tolerance: the reference run without mpiexec) whose shortest-path trees, with the trips hanging off them, are
-dealt round-robin to the GPUs; the daily NCCL all-reduce sums the loads (bit-identical to the 1-GPU result).
+tolerance: the reference run without mpiexec) whose distinct roots, sorted along the Hilbert curve, are cut into one
+contiguous run per GPU (with the trips hanging off them); the daily NCCL all-reduce inside the library sums the loads
+(bit-identical to the 1-GPU result: every line carries `load_hash`).
 --scaling weak: one virtual rank with its own trips and jam tolerance per GPU (streets4mpi.py:50-51,69,78);
 --scaling ranks: the 1M trips divided over per-GPU virtual ranks, every rank needing its own trees.
 
@@ -59,8 +60,8 @@ def log(*a):
 def make_workload(name, world, scaling="strong"):
     """scaling == "weak": every GPU (= one virtual rank with its own trip stream and jam tolerance) routes the
     workload's full day, the job routes world x that.  "strong": ONE virtual rank (one trip list, one jam
-    tolerance -- the reference started without mpiexec) whose shortest-path trees are dealt round-robin to the
-    GPUs (distributed.partition_by_root); the all-reduce sums the loads.  "ranks": the day's trips divided over
+    tolerance -- the reference started without mpiexec) whose roots are cut into one contiguous run per GPU
+    (distributed.partition_by_root); the all-reduce sums the loads.  "ranks": the day's trips divided over
     per-GPU virtual ranks like streets4mpi.py:69 divides number_of_residents (every rank needs its own trees)."""
     from streets4mpi_b200 import synth
     rows, cols, trips_total = WORKLOADS[name]
