@@ -5,10 +5,14 @@
 // distance words, shared-memory frontier staging, warp ballot compaction and a
 // persistent grid sized to the SM count.
 //
-//   K1  weights_street_kernel / weights_arc_kernel   simulation.py:53-65, :129-138
-//   K2  sssp_nearfar_kernel                          simulation.py:71-75 -> streetnetwork.py:108-109
-//   K3  walk_kernel                                  simulation.py:78-88
-//   K4b merge kernels                                streets4mpi.py:100, utils.py:26-34
+//   K1  weights_street_kernel / weight_scale_kernel / weights_arc_kernel / weights_ellw_kernel
+//                                                    simulation.py:53-65, :129-138
+//   K2  sssp_group_kernel (s4_sssp_group.cuh: 15 / 31 trees per CTA or cluster on one shared frontier);
+//       sssp_nearfar_kernel (here: one tree per CTA, round 1, still selectable)
+//                                                    simulation.py:71-75 -> streetnetwork.py:108-109
+//   K3  walk_kernel / walk_slow_kernel (here); pred_code_kernel / walk_code_kernel (s4_walk_codes.cuh)
+//                                                    simulation.py:78-88
+//   K4b merge kernels (the all-reduce itself is NCCL, s4_capi.cu)      streets4mpi.py:100, utils.py:26-34
 //   K5  adapt_kernel                                 simulation.py:91-109, streetnetwork.py:79-82
 #pragma once
 

@@ -36,7 +36,14 @@ for r in range(N):
         c = sim.counters()
         sim.commit_total()
     slots, K = sim.root_slots()
-    print(json.dumps({"rank": r, "trips": len(od), "trees": sim.n_roots, "groups": len(slots) // K, "K": K, "wall_ms": round(wall, 1),
+    extra = {}
+    gl = g.group_log().astype(np.float64)
+    if len(gl):
+        msg = gl[:, 0] * 1024 / 1.965e6
+        extra = {"group_ms_pct": [round(float(x), 1) for x in np.percentile(msg, [0, 50, 90, 99, 100])],
+                 "group_ms_sum_over_sms": round(float(msg.sum()) / 148, 1), "first_groups_ms": [round(float(x), 1) for x in msg[:6]],
+                 "last_groups_ms": [round(float(x), 1) for x in msg[-6:]]}
+    print(json.dumps({"rank": r, **extra, "trips": len(od), "trees": sim.n_roots, "groups": len(slots) // K, "K": K, "wall_ms": round(wall, 1),
                       "ms_sssp": round(c["ms_sssp"], 1), "ms_walk": round(c["ms_walk"], 1), "launches": c["sssp_launches"],
                       "fb": c["fallback_sweeps"]}), flush=True)
     sim.close()
