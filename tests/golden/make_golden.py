@@ -25,6 +25,14 @@ What is executed verbatim from /root/reference:
                     tagged nodes only, ways (id, tags, refs), relations (id, tags,
                     [(ref, type, role)]).  The construction rules, the speed table, the
                     haversine and the landuse closure are the reference's code (osm_ingest.json).
+  visualization.py  source text up to its ``__main__`` block with the Python-2 syntax made runnable (``print``
+                    statements -> calls, ``xrange`` -> ``range``, the three integer divisions of the legend
+                    geometry -> ``//``, ``filter`` returning lists), ``persistence.persist_read`` serving the
+                    fixture's objects, ``draw.textsize`` shimmed (gone from Pillow 10).  What is recorded is
+                    WHAT IT DRAWS, not the pixels: every street line (end points as fp64 hex, fill colour) and
+                    the zoom, for four modes x two colour modes (visualization.json).  COMPONENTS is left out:
+                    the reference's own ``dict(edge_attributes(street))`` raises on the attribute list its
+                    StreetNetwork stores (visualization.py:132).
 Nothing else is shimmed: weights, the walk, the load counters, the adaptation
 sweep and the speed clamp are the reference's code paths.
 """
@@ -185,6 +193,109 @@ def osm_record(name, xml_text, osmdata_mod):
             "connected_residential": sorted(b.connected_residential_nodes),
             "connected_industrial": sorted(b.connected_industrial_nodes),
             "connected_commercial": sorted(b.connected_commercial_nodes)}
+
+
+def gen_visualization(out_dir, streetnetwork, sim_mod):
+    """visualization.py:67-141 executed on a small network and two days of loads: the street lines it draws."""
+    import builtins
+    import re
+    import tempfile
+    from PIL import ImageDraw
+    text = open(os.path.join(REF, "visualization.py")).read()
+    text = text[:text.index('if __name__ == "__main__":')]
+    text = re.sub(r"^(\s*)print (.*)$", r"\1print(\2)", text, flags=re.M)
+    assert "print " not in re.sub(r"#.*", "", text)
+    text = text.replace("xrange(", "range(")
+    for old, new in (("self.max_resolution[0] / 40", "self.max_resolution[0] // 40"),
+                     ("self.max_resolution[0] / 50", "self.max_resolution[0] // 50"),
+                     ("int(bar_outer_width - bar_inner_width) / 2", "int(bar_outer_width - bar_inner_width) // 2")):
+        assert text.count(old) == 1
+        text = text.replace(old, new)
+    rng = random.Random(77)
+    nodes = [(100 + i, 9.90 + 0.002 * (i % 6) + rng.uniform(-4e-4, 4e-4), 53.55 + 0.0015 * (i // 6) + rng.uniform(-3e-4, 3e-4))
+             for i in range(30)]
+    streets = []
+    for i in range(30):
+        if i % 6 != 5:
+            streets.append((100 + i, 100 + i + 1))
+        if i + 6 < 30:
+            streets.append((100 + i + 6, 100 + i) if i % 4 == 0 else (100 + i, 100 + i + 6))
+    speeds = [rng.choice([1, 20, 30, 50, 70, 100, 140]) for _ in streets]
+    lengths = [rng.uniform(40.0, 300.0) for _ in streets]
+    loads = [[rng.choice([0, 0, 1, 3, 10, 40, 150]) for _ in streets] for _day in range(2)]
+    net = streetnetwork.StreetNetwork()
+    for (n, lon, lat) in nodes:
+        net.add_node(n, lon, lat)
+    net.set_bounds(min(x[2] for x in nodes), max(x[2] for x in nodes), min(x[1] for x in nodes), max(x[1] for x in nodes))
+    for (st, L, ms) in zip(streets, lengths, speeds):
+        net.add_street(st, L, ms)
+    files = {"street_network_1.s4mpi": net, "traffic_load_1.s4mpi": array("I", loads[0]), "traffic_load_2.s4mpi": array("I", loads[1])}
+    pers = types.ModuleType("persistence")
+    pers.persist_read = lambda filename, is_array=False: files[filename]
+    sys.modules["persistence"] = pers
+    acc = types.ModuleType("pygraph.algorithms.accessibility")
+    acc.connected_components = lambda g: {}
+    sys.modules["pygraph.algorithms.accessibility"] = acc
+    if not hasattr(ImageDraw.ImageDraw, "textsize"):
+        def textsize(self, text, font=None):
+            box = self.textbbox((0, 0), text, font=font)
+            return box[2] - box[0], box[3] - box[1]
+        ImageDraw.ImageDraw.textsize = textsize
+    mod = types.ModuleType("ref_visualization")
+    mod.__file__ = os.path.join(REF, "visualization.py")
+    mod.filter = lambda f, xs: list(builtins.filter(f, xs))
+    mod.print = lambda *a: None
+    exec(compile(text, mod.__file__, "exec"), mod.__dict__)
+    recs = []
+    real_line = ImageDraw.ImageDraw.line
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as d:
+        os.chdir(d)
+        try:
+            for name in files:
+                open(name, "w").close()
+            for mode in ("TRAFFIC_LOAD", "MAX_SPEED", "IDEAL_SPEED", "ACTUAL_SPEED"):
+                for color_mode in ("HEATMAP", "MONOCHROME"):
+                    vis = mod.Visualization("^street_network_[0-9]+.s4mpi$", "^traffic_load_[0-9]+.s4mpi$", mode=mode, color_mode=color_mode)
+                    drawn, in_legend = [], [False]
+                    fin = vis.image_finalize
+
+                    def finalize(image, max_load, fin=fin, in_legend=in_legend):
+                        in_legend[0] = True
+                        try:
+                            return fin(image, max_load)
+                        finally:
+                            in_legend[0] = False
+                            drawn.append("end of step")
+                    vis.image_finalize = finalize
+
+                    def line(self, xy, fill=None, width=0, joint=None, in_legend=in_legend, drawn=drawn):
+                        if not in_legend[0]:
+                            drawn.append([[hexf(xy[0][0]), hexf(xy[0][1]), hexf(xy[1][0]), hexf(xy[1][1])],
+                                          fill if isinstance(fill, str) else list(fill), width])
+                        return real_line(self, xy, fill=fill, width=width)
+                    ImageDraw.ImageDraw.line = line
+                    try:
+                        vis.visualize()
+                    finally:
+                        ImageDraw.ImageDraw.line = real_line
+                    steps, cur = [], []
+                    for item in drawn:
+                        if item == "end of step":
+                            steps.append(cur)
+                            cur = []
+                        else:
+                            cur.append(item)
+                    order = [[st[0], st[1]] for (st, _i, _l, _m) in net]
+                    recs.append({"mode": mode, "color_mode": color_mode, "zoom": hexf(vis.zoom), "iteration_order": order,
+                                 "lines_per_step": steps})
+        finally:
+            os.chdir(cwd)
+    json.dump({"source": "visualization.py Visualization.visualize executed under Python 3 (print / xrange / three integer "
+                         "divisions adapted); recorded: the street lines handed to ImageDraw.line, in iteration order",
+               "nodes": [[n, hexf(lon), hexf(lat)] for (n, lon, lat) in nodes],
+               "streets": [[st[0], st[1], hexf(L), ms] for (st, L, ms) in zip(streets, lengths, speeds)],
+               "loads": loads, "cases": recs}, open(os.path.join(out_dir, "visualization.json"), "w"))
 
 
 def gen_osm_ingest(out_dir):
@@ -417,6 +528,7 @@ def main():
                "a_none": list(utils.merge_arrays((a, None)))},
               open(os.path.join(out_dir, "merge_arrays.json"), "w"))
     gen_osm_ingest(out_dir)
+    gen_visualization(out_dir, streetnetwork, sim)
     print("golden fixtures written to", out_dir)
 
 

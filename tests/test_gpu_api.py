@@ -315,3 +315,16 @@ def test_stuck_trips_are_surfaced():
     want, cnt = ctwin.day(csr, w, flat.dense([0, 0]), flat.dense([n, 5]))
     assert cnt["stuck"] == 1 and sim.counters()["trips_stuck"] == 1
     assert np.array_equal(load, want) and load[0] == 1     # the trip to node 5 is 4 plateau nodes from its exit
+
+
+def test_visualization_speed_modes_draw_what_the_reference_draws(tmp_path):
+    """The two speed modes of the heat maps evaluate calculate_driving_speed (simulation.py:129-138) per street -- on the
+    device here: same lines, same colours as the reference's visualization.py drew (tests/golden/visualization.json)."""
+    from tests.helpers import visualization_lines
+    runs = visualization_lines("visualization.json", tmp_path, ("IDEAL_SPEED", "ACTUAL_SPEED"))
+    assert len(runs) == 4
+    for case, zoom, steps in runs:
+        assert zoom == case["zoom"] and len(steps) == 2
+        for got, want in zip(steps, case["lines_per_step"]):
+            key = lambda rec: tuple(rec[0])
+            assert sorted(got, key=key) == sorted(want, key=key), (case["mode"], case["color_mode"])

@@ -170,3 +170,46 @@ def test_cfg4_road_graph_at_5m_nodes():
     finally:
         dev.set_option("root_mode", old)
     g.close()
+
+
+def test_cluster_shared_groups_at_scale():
+    """The large-graph configuration (BASELINE configs[4]: a slot per group is gigabytes, fewer slots than SMs, so the
+    CTAs of a thread-block cluster share one group) forced onto a 4 M-node road-like graph: two whole trees bit-equal
+    to the oracle's, and a day of 4 k trips from 60 residential origins bit-equal to the oracle's load."""
+    from oracle import ctwin
+    from streets4mpi_b200 import engine, synth
+    from streets4mpi_b200.settings import settings
+    dev = engine.default_device()
+    phys = engine.make_physics(settings)
+    arr = synth.ladder_arrays(2000, 2000, seed=3)
+    flat = synth.network_from(arr).flat()
+    keys = ("cluster", "block_threads", "group_words", "root_mode")
+    old = {k: dev.get_option(k) for k in keys}
+    try:
+        dev.set_option("group_words", 2)
+        dev.set_option("block_threads", 1024)
+        dev.set_option("cluster", 4)
+        dev.set_option("root_mode", 0)
+        g = engine.DeviceGraph(dev, flat.V, flat.u, flat.v, flat.length, flat.max_speed, node_rank=flat.locality_rank())
+        csr = ctwin.Csr(flat.V, flat.u, flat.v)
+        rng = np.random.default_rng(7)
+        w = rng.uniform(0.1, 13.0, size=flat.S)
+        for src in (3, flat.V // 2 + 999):
+            dist, pred = g.sssp(w, src)
+            d0, p0, _ = ctwin.sssp(csr, w, src)
+            assert np.array_equal(dist.view(np.uint64), d0.view(np.uint64))
+            assert np.array_equal(pred, p0)
+        cats = synth.node_categories(arr["node_ids"], seed=3, goal_fraction=0.02, residential_fraction=60.5 / flat.V)
+        o, gl = synth.trip_arrays(4000, cats["residential"], cats["goals"], seed=11)
+        sim = engine.DeviceSim(g, flat.dense(o), flat.dense(gl), 0.4, phys)
+        sim.step()
+        c = sim.counters()
+        w0 = ctwin.weights(flat.length, flat.max_speed, np.zeros(flat.S, dtype=np.uint32), 0.4)
+        want, cnt = ctwin.day(csr, w0, flat.dense(o), flat.dense(gl), nthreads=16)
+        assert cnt["tied_trips"] == 0 and c["trips_unreachable"] == cnt["unreachable"] and c["hops"] == cnt["hops"]
+        assert np.array_equal(sim.get_load(), want)
+        sim.close()
+        g.close()
+    finally:
+        for k, val in old.items():
+            dev.set_option(k, val)

@@ -312,6 +312,22 @@ def test_osm_ingest_matches_reference_fixture(tmp_path):
         assert flat.max_speed.tolist() == [s[3] for s in case["streets"]]
 
 
+def test_visualization_draws_what_the_reference_draws(tmp_path):
+    """f4 pinned where it is meaningful: tests/golden/visualization.json records every street line the reference's
+    own visualization.py hands to ImageDraw (end points as fp64 hex, colour) for a small network and two days of
+    loads; this package's Visualization must draw the same lines in the same colours (the device-free modes here,
+    the two speed modes in tests/test_gpu_api.py)."""
+    from tests.helpers import visualization_lines
+    runs = visualization_lines("visualization.json", tmp_path, ("TRAFFIC_LOAD", "MAX_SPEED"))
+    assert len(runs) == 4
+    for case, zoom, steps in runs:
+        assert zoom == case["zoom"]
+        assert len(steps) == len(case["lines_per_step"]) == 2
+        for got, want in zip(steps, case["lines_per_step"]):
+            key = lambda rec: tuple(rec[0])
+            assert sorted(got, key=key) == sorted(want, key=key), (case["mode"], case["color_mode"])
+
+
 def test_visualization_modes_without_gpu(tmp_path):
     """The offline heat maps read the .s4mpi files and write one PNG per day (no device needed for the
     load / speed-limit / component modes)."""
