@@ -124,7 +124,8 @@ int s4_ctx_sync(s4_ctx *ctx);
  *   "balance_waves"      1 (default): fewer trees per group when that fills the last wave of a launch
  *   "cluster"            0 (default: from the number of slots that fit in the pool) | 1 | 2 | 4 | 8: CTAs of a
  *                        thread-block cluster that share one group (graphs with 10^7 .. 10^8 nodes: fewer slots than SMs)
- *   "walk_codes"         2 (default): with at least 150 trips per tree a streaming pass writes the predecessor of every
+ *   "walk_codes"         2 (default): when the day's walks are long against a pass over every (node, tree) -- hops of the
+ *                        previous day (first day: trips x half the graph's hop depth) >= 0.1 * V * trees -- a streaming pass writes the predecessor of every
  *                        (node, tree) as a 2-bit arc-slot code into the rows' meta words and the walks take one lane and
  *                        one dependent access per hop; 1: always; 0: never (predecessors derived on the fly)
  *   "l2_persist"         1: access-policy window that keeps the arc rows in L2 (measured: no gain; default 0)

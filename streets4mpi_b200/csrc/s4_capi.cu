@@ -169,6 +169,7 @@ struct s4_graph {
     std::vector<int32_t> max_speed0;   // host copy of the uploaded limits
     std::vector<u32> row_ptr_h, col_h;  // host copy of the CSR (device numbering): root clustering at simulation setup
     std::vector<u32> gorder_h, ginv_h;  // grouping order of tree roots: device number -> position / position -> device number
+    double mean_ecc = 0.0;              // mean of ecc_h
     std::vector<int32_t> ecc_h;         // hops to the farther end of the graph's longest BFS path (depth of a tree rooted here)
     DevBuf<u32> gorder, ginv;
     // connected components (host): algorithmic arcs / nodes of a tree rooted at r
@@ -684,7 +685,12 @@ extern "C" int s4_graph_upload(s4_ctx *ctx, int32_t V, int64_t S, const int32_t 
             // how deep a tree rooted at a node is, in hops (the two ends of the longest BFS path bound it from below):
             // groups of trees are started longest-first when a launch has only a few waves of them
             g->ecc_h.resize((size_t)V);
-            for (int32_t i = 0; i < V; ++i) g->ecc_h[(size_t)i] = std::max(0, std::max(da[(size_t)i], db[(size_t)i]));
+            double ecc_sum = 0.0;
+            for (int32_t i = 0; i < V; ++i) {
+                g->ecc_h[(size_t)i] = std::max(0, std::max(da[(size_t)i], db[(size_t)i]));
+                ecc_sum += (double)g->ecc_h[(size_t)i];
+            }
+            g->mean_ecc = ecc_sum / (double)V;
             int32_t c_node = far1;
             int32_t best_min = -1;
             for (int32_t i = 0; i < V; ++i) {
@@ -1814,8 +1820,17 @@ extern "C" int s4_sim_step(s4_sim *sim)
     // that their number fills whole waves (4 % head room: the greedy clustering leaves some groups short).
     int K_fill = (int)K;
     int64_t waves_wanted = 0;                                      // 0: many waves, their number does not matter
+    // groups that run at the same time: one per SM (or cluster), and no more than the pool has slots for
+    int64_t W_run = std::max(1, L.units());
+    {
+        double pool_budget = 0.0, ws_budget = 0.0;
+        if ((rc = scratch_budget(g, &pool_budget, &ws_budget))) return rc;
+        const int64_t by_mem = (int64_t)(pool_budget / (8.0 * (double)slot_words(g, L.lay)));
+        const int64_t cap = ctx->opt.batch_roots > 0 ? std::min<int64_t>(std::max<int64_t>(1, ctx->opt.batch_roots / K), by_mem) : by_mem;
+        W_run = std::max<int64_t>(1, std::min<int64_t>(W_run, cap));
+    }
     if (K > 1 && sim->D > 0 && ctx->opt.balance_waves) {
-        const int64_t W = std::max(1, L.units());
+        const int64_t W = W_run;
         const int64_t G0 = (sim->D + K - 1) / K, waves = (G0 + W - 1) / W;
         const double target = 0.96 * (double)(waves * W);
         K_fill = (int)std::min<int64_t>(K, std::max<int64_t>(1, (int64_t)std::ceil((double)sim->D / std::max(1.0, target))));
@@ -1830,7 +1845,7 @@ extern "C" int s4_sim_step(s4_sim *sim)
         int fill = K_fill;
         for (int attempt = 0;; ++attempt) {
             if ((rc = sim_regroup(sim, (int)K, fill, few_waves))) return rc;
-            if (!few_waves || sim->Dp / K <= waves_wanted * (int64_t)std::max(1, L.units()) || fill >= (int)K || attempt >= 12) break;
+            if (!few_waves || sim->Dp / K <= waves_wanted * W_run || fill >= (int)K || attempt >= 12) break;
             ++fill;
         }
         sim->grouped_fill0 = K_fill;
@@ -1901,7 +1916,7 @@ extern "C" int s4_sim_step(s4_sim *sim)
     }
     // predecessor codes pay when the walks are long against the streaming pass over V x trees words: measured on cfg3 the
     // pass costs what 0.1 * V * D hops cost the eight-lane walk.  Hops of the last day whose counter has arrived;
-    // before that, 150 trips per tree (700-hop trips on cfg3).
+    // before that, trips x half the mean hop depth of a tree (720 hops per trip on cfg3: the estimate says 770).
     if (!sim->hops_host) {
         CU(cudaHostAlloc((void **)&sim->hops_host, sizeof(u64), cudaHostAllocDefault));
         *sim->hops_host = 0;
@@ -1911,8 +1926,8 @@ extern "C" int s4_sim_step(s4_sim *sim)
         if (now > sim->hops_seen) { sim->hops_per_day = (double)(now - sim->hops_seen); sim->hops_seen = now; }
         else if (now < sim->hops_seen) { sim->hops_seen = now; }                    // counters were reset
     }
-    const bool codes_pay = sim->hops_per_day > 0.0 ? sim->hops_per_day >= 0.1 * (double)g->V * (double)std::max<int64_t>(1, sim->D)
-                                                   : sim->T >= 150 * std::max<int64_t>(1, sim->D);
+    const double hops_expected = sim->hops_per_day > 0.0 ? sim->hops_per_day : 0.5 * g->mean_ecc * (double)sim->T;
+    const bool codes_pay = hops_expected >= 0.1 * (double)g->V * (double)std::max<int64_t>(1, sim->D);
     const size_t sw = slot_words(g, L.lay);
     for (int64_t bi = 0; bi < n_batches; ++bi) {
         const int64_t r0 = bi * B * K, r1 = std::min(D, r0 + B * K);

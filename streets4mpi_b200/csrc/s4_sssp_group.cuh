@@ -220,11 +220,21 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? (TL 
     const u32 unit = CL > 1 ? blockIdx.x / (u32)CL : blockIdx.x;
     u32 *const ctl = CL > 1 ? p.cluster_ctl + (size_t)unit * GC_WORDS : nullptr;
     const bool lead = tid == 0 && crank == 0u;                    // the one thread that owns the shared control state
-    auto CNT = [&](u32 i) -> u32 * { if constexpr (CL > 1) return ctl + GC_CNT + i; else return &s_cnt[i]; };
-    auto FAR_CNT = [&](u32 i) -> u32 * { if constexpr (CL > 1) return ctl + GC_FAR_CNT + i; else return &s_far_cnt[i]; };
-    auto FAR_MIN = [&](u32 i) -> u32 * { if constexpr (CL > 1) return ctl + GC_FAR_MIN + i; else return &s_far_min[i]; };
-    auto OVERFLOW = [&]() -> u32 * { if constexpr (CL > 1) return ctl + GC_OVERFLOW; else return &s_overflow; };
-    auto rd = [&](const u32 *q) -> u32 { if constexpr (CL > 1) return __ldcg(q); else return *q; };
+    // the queue counters of a cluster live in the shared memory of its first CTA and are reached through distributed
+    // shared memory (an atomic there returns in ~215 cycles, a global one in ~700: it sits on every pass's push)
+    u32 *cl_cnt = s_cnt, *cl_far_cnt = s_far_cnt, *cl_far_min = s_far_min, *cl_overflow = &s_overflow;
+    if constexpr (CL > 1) {
+        cg::cluster_group cluster = cg::this_cluster();
+        cl_cnt = cluster.map_shared_rank(s_cnt, 0);
+        cl_far_cnt = cluster.map_shared_rank(s_far_cnt, 0);
+        cl_far_min = cluster.map_shared_rank(s_far_min, 0);
+        cl_overflow = cluster.map_shared_rank(&s_overflow, 0);
+    }
+    auto CNT = [&](u32 i) -> u32 * { if constexpr (CL > 1) return cl_cnt + i; else return &s_cnt[i]; };
+    auto FAR_CNT = [&](u32 i) -> u32 * { if constexpr (CL > 1) return cl_far_cnt + i; else return &s_far_cnt[i]; };
+    auto FAR_MIN = [&](u32 i) -> u32 * { if constexpr (CL > 1) return cl_far_min + i; else return &s_far_min[i]; };
+    auto OVERFLOW = [&]() -> u32 * { if constexpr (CL > 1) return cl_overflow; else return &s_overflow; };
+    auto rd = [&](const u32 *q) -> u32 { if constexpr (CL > 1) return *reinterpret_cast<const volatile u32 *>(q); else return *q; };
     auto sync_all = [&]() { if constexpr (CL > 1) cg::this_cluster().sync(); else __syncthreads(); };
     u32 *wv = p.ws_v + (size_t)unit * ws_stride;
     u32 *wk = p.ws_k + (size_t)unit * ws_stride;
@@ -318,6 +328,11 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? (TL 
                 const u32 rid_next = rid + 1u;
                 const double thr_up = __hiloint2double((int)(thr_hi + 1u), 0);   // upper end of the bucket
                 const double lag = s_lag;
+                u32 u_next = 0u;                                            // cluster: the entry of the next pass, fetched a pass ahead
+                if constexpr (CL > 1) {
+                    const u32 i0 = crank * PW + sub;
+                    if (i0 < n_s) u_next = __ldcg(wv + cur_off + i0);
+                }
                 for (u32 base = 0; base < n_s; base += PW * (u32)CL) {
                     const u32 i = base + crank * PW + sub;
                     const bool valid = i < n_s;                             // uniform in the sub-warp
@@ -329,8 +344,13 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? (TL 
 #pragma unroll
                     for (int j = 0; j < kEllWidth; ++j) { a[j].col = 0u; a[j].street = 0u; a[j].w = 0.0; }
                     if (valid) {
-                        if constexpr (CL > 1) u = __ldcg(wv + cur_off + i);          // written by any CTA of the cluster
-                        else u = i < scap ? csv[i] : wv[cur_off + i];
+                        if constexpr (CL > 1) {
+                            // written by any CTA of the cluster (global workspace); a global read would be one more
+                            // dependent stage in front of the row loads, so it was issued during the previous pass
+                            u = u_next;
+                            const u32 i_next = i + PW * (u32)CL;
+                            if (i_next < n_s) u_next = __ldcg(wv + cur_off + i_next);
+                        } else u = i < scap ? csv[i] : wv[cur_off + i];
                         const Arc *row = p.ellw + (size_t)u * kEllWidth;
                         ld_row_half(row, a[0], a[1]);
                         ld_row_half(row + 2, a[2], a[3]);
