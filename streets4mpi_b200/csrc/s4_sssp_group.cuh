@@ -496,8 +496,11 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK <= 32 ? 32 : BLOCK <= 512 ? (TL 
                 if (p.adaptive) {
                     const u32 br = s_bucket_rounds, be = s_bucket_entries;
                     if (br > 0u) {
-                        if (be < br * (PW * (u32)CL / 2u) && dmul < 16.0) dmul *= 1.5;
-                        else if (be > br * (PW * (u32)CL * 4u) && dmul > 1.0) dmul *= (1.0 / 1.5);
+                        // a cluster widens its buckets only half as eagerly as its width would suggest: wider buckets
+                        // mean more re-expansions (cfg3, two CTAs per group: 1.73x -> the work of one CTA's buckets)
+                        constexpr u32 AW = PW * (CL > 1 ? (u32)CL / 2u : 1u);
+                        if (be < br * (AW / 2u) && dmul < 16.0) dmul *= 1.5;
+                        else if (be > br * (AW * 4u) && dmul > 1.0) dmul *= (1.0 / 1.5);
                     }
                 }
                 double delta = p.delta_scale * __ldg(p.wsum);
