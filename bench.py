@@ -493,13 +493,14 @@ def gpu_arm(args):
     # events around every launch time that kernel and nothing else (in the timed region above two launch
     # lanes overlap, which is faster but makes per-launch times meaningless)
     barrier()
+    lanes_default = dev.get_option("lanes")
     dev.set_option("lanes", 1)
     sim._sim.reset_counters()
     with torch.cuda.stream(stream):
         day_resident()
     barrier()
     cs = sim.counters()
-    dev.set_option("lanes", 2)
+    dev.set_option("lanes", lanes_default)
     # what every GPU did (rank 0 prints it): a day ends with an all-reduce, so the slowest GPU sets the pace
     slots_r, k_r = sim._sim.root_slots()
     mine = {"rank": rank, "trees": int(sim._sim.n_roots), "groups": int(len(slots_r) // max(1, k_r)), "trees_per_group_slots": int(k_r),
@@ -545,7 +546,7 @@ def gpu_arm(args):
         one()
         barrier()
         cy = sim_x.counters()
-        dev.set_option("lanes", 2)
+        dev.set_option("lanes", lanes_default)
         algb = 20.0 * cy["arcs_algorithmic"] + 20.0 * cy["nodes_algorithmic"]
         frac = algb / (cy["ms_sssp"] * 1e-3) / 1e9 / peak_gbs if cy["ms_sssp"] > 0 else None
         return {"ms_per_day": ms_day, "trips_per_sec": trips_d / (ms_day * 1e-3), "trees_per_day": trees_d,
